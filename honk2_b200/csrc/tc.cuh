@@ -1,0 +1,19 @@
+// Interface of the bf16 tensor-core (tcgen05 / TMEM / TMA) ResNet path, conv_tc.cu.
+#pragma once
+#include "common.cuh"
+
+namespace kws {
+
+struct TcResNet;  // opaque plan: packed bf16 weights, tensor maps, geometry
+
+int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out);
+void tc_resnet_destroy(TcResNet* p);
+// w: torch-layout fp32 device tensors; bn_scale/bn_shift: per-layer [C] device vectors that
+// the caller already derived from running_mean / running_var.
+int tc_resnet_set_weights(TcResNet* p, const kws_resnet_weights& w, float* const* bn_scale,
+                          float* const* bn_shift, cudaStream_t st);
+size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int chunk);
+int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, float* logits, void* ws,
+                      size_t ws_bytes, int chunk, LaunchProfiler* prof, cudaStream_t st);
+
+}  // namespace kws

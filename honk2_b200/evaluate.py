@@ -1,0 +1,63 @@
+"""Evaluation loops.
+
+``evaluate`` keeps the signature and result keys of the reference's
+(/root/reference/run/test.py:18-41) so it can replace it under run/train.py:162,203; the loss is
+accumulated on the device and read once at the end instead of ``.item()`` per batch.
+
+``evaluate_waves`` is the batched form the reference approximates with DataLoader workers +
+DataParallel: raw waveforms in, logits and accuracy out, sharded across ranks (dist.py).
+"""
+import torch
+
+from .dist import all_gather_rows, shard_bounds, world
+from .metric import Acc
+
+
+def evaluate(device, prefix, model, data_loader, loss_fn, metrics, label_mapping):
+    total_loss = None
+    n_batches = 0
+    model.eval()
+    for data, target in data_loader:
+        data, target = data.to(device, non_blocking=True), target.to(device, non_blocking=True)
+        with torch.no_grad():
+            output = model(data)
+            loss = loss_fn(output, target)
+        total_loss = loss.detach() if total_loss is None else total_loss + loss.detach()
+        n_batches += 1
+        for metric in metrics.values():
+            metric.accumulate(output, target)
+    results = {"loss": (float(total_loss) / n_batches) if n_batches else float("nan")}
+    for name, metric in metrics.items():
+        value = metric.get_metric()
+        if isinstance(value, dict):  # per-class metrics are re-keyed by label (metric_utils.py:44-50)
+            value = {label_mapping[k]: v for k, v in value.items()}
+        results[f"metric_{name}"] = value
+    return results
+
+
+def evaluate_waves(model, audio_processor, waves, targets=None, batch_size=8192, device=None):
+    """waves: [N, n_samples] float32 (CPU pinned or CUDA); this rank evaluates its contiguous
+    shard in batches and returns (logits [N, n_labels] on every rank, accuracy or None)."""
+    rank, ws = world()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    n = waves.shape[0]
+    lo, hi = shard_bounds(n, rank, ws)
+    acc = Acc()
+    outs = []
+    model.eval()
+    with torch.no_grad():
+        for b0 in range(lo, hi, batch_size):
+            b1 = min(hi, b0 + batch_size)
+            w = waves[b0:b1].to(device, non_blocking=True)
+            logits = model.forward_wave(w, audio_processor)
+            outs.append(logits)
+            if targets is not None:
+                acc.accumulate(logits, targets[b0:b1].to(device, non_blocking=True))
+    local = torch.cat(outs) if outs else torch.empty((0, model.n_labels), dtype=torch.float32, device=device)
+    full = all_gather_rows(local, n)
+    accuracy = None
+    if targets is not None:
+        if acc._counts is None:
+            acc._counts = torch.zeros(2, dtype=torch.int64, device=device)
+        accuracy = acc.all_reduce().get_metric()
+    return full, accuracy

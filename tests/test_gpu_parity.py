@@ -1,0 +1,213 @@
+"""GPU parity tests proper: everything goes through the C-ABI library (ctypes) and is checked
+against the CPU oracle / the committed goldens.  Tolerances are BASELINE.json's:
+  MFCC features   |a-b| <= 1e-4 * max(|b|, 1)
+  fp32 logits     |a-b| <= 1e-3 * max(|b|_inf per row, 1e-3), identical argmax
+"""
+import numpy as np
+import pytest
+import torch
+
+import honk2_b200
+from conftest import logit_err, scaled_err
+from honk2_b200 import AudioProcessor, synth
+from honk2_b200.zoo import MODEL_ZOO, model_config
+from oracle import mfcc_ref, model_ref
+
+pytestmark = pytest.mark.gpu
+
+MFCC_TOL = 1e-4
+LOGIT_TOL = 1e-3
+ZOO = list(MODEL_ZOO)
+RESNETS = [n for n in ZOO if MODEL_ZOO[n]["name"] == "ResNet"]
+
+
+@pytest.fixture(scope="module")
+def dev(native_lib):
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch.device("cuda", 0)
+
+
+def gpu_model(name, variant, dev, precision="fp32"):
+    m = honk2_b200.build_model(name, precision=precision)
+    sd = m.state_dict()
+    if variant == "hardened":
+        synth.harden_(sd)
+    return m.to(dev), {k: v.clone() for k, v in sd.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# front-end
+
+def test_mfcc_matches_golden_and_oracle(dev, golden_waves, mfcc_golden):
+    ap = AudioProcessor()
+    for name, w in golden_waves.items():
+        got = ap.compute_mfccs_batch(torch.from_numpy(w.astype(np.float32)).to(dev)).cpu().numpy()
+        ref = mfcc_golden[f"{name}_feat"]
+        assert got.shape == ref.shape
+        assert scaled_err(got, ref) <= MFCC_TOL, (name, scaled_err(got, ref))
+
+
+def test_mfcc_reference_api(dev, golden_waves):
+    """compute_mfccs(np 1-D) -> (T, 40, 1) float32 (audio_processor.py:18-30)."""
+    ap = AudioProcessor()
+    y = golden_waves["broadband"][0]
+    f = ap.compute_mfccs(y)
+    assert f.shape == (101, 40, 1) and f.dtype == np.float32
+    assert scaled_err(f, mfcc_ref.compute_mfccs(y)) <= MFCC_TOL
+    f64 = ap.compute_mfccs(y.astype(np.float64))
+    assert scaled_err(f64, f) <= MFCC_TOL
+    with pytest.raises(ValueError):
+        ap.compute_mfccs(np.zeros(16000, dtype=np.int16))
+    with pytest.raises(ValueError):
+        ap.compute_mfccs(np.full(16000, np.nan, dtype=np.float32))
+
+
+def test_mfcc_zero_input_is_exact_zero(dev):
+    ap = AudioProcessor()
+    f = ap.compute_mfccs_batch(torch.zeros(3, 16000, device=dev))
+    assert torch.count_nonzero(f).item() == 0
+
+
+@pytest.mark.parametrize("n", [241, 480, 1000, 15999, 16000, 16001, 144000])
+def test_mfcc_clip_lengths(dev, n):
+    """T = 1 + N // 160 for any clip length that survives reflect padding (N > 240)."""
+    ap = AudioProcessor()
+    w = synth.broadband(2, N=n, seed=n)
+    got = ap.compute_mfccs_batch(torch.from_numpy(w).to(dev)).cpu().numpy()
+    ref = mfcc_ref.compute_mfccs_batch(w)
+    assert got.shape == ref.shape == (2, 1 + n // 160, 40)
+    assert scaled_err(got, ref) <= MFCC_TOL
+
+
+def test_mfcc_batch_is_per_utterance(dev):
+    """collate semantics: row b of the batch == the single-utterance call."""
+    ap = AudioProcessor()
+    w = torch.from_numpy(synth.speechlike(5, seed=3)).to(dev)
+    full = ap.compute_mfccs_batch(w)
+    for b in range(5):
+        assert torch.equal(full[b], ap.compute_mfccs_batch(w[b:b + 1])[0])
+
+
+def test_mfcc_large_batch_statistics(dev):
+    """BASELINE size (8192 x 1 s): spot-check 16 random rows against the oracle."""
+    ap = AudioProcessor()
+    w = synth.broadband(8192, seed=5)
+    got = ap.compute_mfccs_batch(torch.from_numpy(w).to(dev))
+    idx = np.random.default_rng(0).choice(8192, 16, replace=False)
+    ref = mfcc_ref.compute_mfccs_batch(w[idx])
+    assert scaled_err(got[torch.from_numpy(idx).to(dev)].cpu().numpy(), ref) <= MFCC_TOL
+    assert torch.isfinite(got).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# models, fp32 path
+
+@pytest.mark.parametrize("name", ZOO)
+@pytest.mark.parametrize("variant", ["default", "hardened"])
+def test_fp32_logits_match_reference_golden(dev, name, variant, model_golden):
+    m, _ = gpu_model(name, variant, dev)
+    x = torch.from_numpy(model_golden["feats"]).to(dev)
+    with torch.no_grad():
+        y = m(x).cpu().numpy()
+    ref = model_golden[f"{name}/{variant}/logits"]
+    assert y.shape == ref.shape
+    assert logit_err(y, ref) <= LOGIT_TOL, (name, variant, logit_err(y, ref))
+    assert np.array_equal(y.argmax(1), ref.argmax(1))
+
+
+@pytest.mark.parametrize("name", RESNETS)
+def test_fp32_resnet_other_time_lengths(dev, name, model_golden):
+    m, _ = gpu_model(name, "hardened", dev)
+    with torch.no_grad():
+        y = m(torch.from_numpy(model_golden["feats_long"]).to(dev)).cpu().numpy()
+    ref = model_golden[f"{name}/hardened/logits_long"]
+    assert logit_err(y, ref) <= LOGIT_TOL
+
+
+@pytest.mark.parametrize("name", ["res8", "res15", "res15_narrow", "res26", "cnn-trad-fpool3", "cnn-one-fstride4"])
+def test_fp32_vs_oracle_seeded_batch(dev, name):
+    """Same seeded inputs through the CUDA path and the CPU oracle; ragged batch, chunking."""
+    kind, cfg = model_config(name)
+    m, sd = gpu_model(name, "hardened", dev)
+    feats = mfcc_ref.compute_mfccs_batch(synth.noisy_dataset_like(7, seed=9))
+    x = torch.from_numpy(feats)
+    ref = model_ref.forward(kind, sd, cfg, x).numpy()
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu().numpy()
+        m.chunk = {"fp32": 3, "bf16": 3}          # 7 = 3 + 3 + 1
+        y_chunked = m(x.to(dev)).cpu().numpy()
+        y1 = m(x[:1].to(dev)).cpu().numpy()
+    assert logit_err(y, ref) <= LOGIT_TOL
+    assert np.array_equal(y.argmax(1), ref.argmax(1))
+    assert np.array_equal(y, y_chunked), "chunking must not change results"
+    assert np.array_equal(y[:1], y1), "utterances are independent"
+
+
+def test_empty_batch(dev):
+    m, _ = gpu_model("res8", "default", dev)
+    with torch.no_grad():
+        assert m(torch.empty(0, 101, 40, device=dev)).shape == (0, 12)
+
+
+def test_cnn_rejects_wrong_geometry(dev):
+    m, _ = gpu_model("cnn-trad-fpool3", "default", dev)
+    with pytest.raises(honk2_b200.NativeError):
+        m(torch.zeros(2, 100, 40, device=dev))
+
+
+def test_weights_follow_load_state_dict(dev, model_golden):
+    """load_state_dict after the first forward must reach the packed device weights."""
+    m, _ = gpu_model("res8", "default", dev)
+    x = torch.from_numpy(model_golden["feats"]).to(dev)
+    with torch.no_grad():
+        m(x)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        synth.harden_(sd)
+        m.load_state_dict(sd)
+        y = m(x).cpu().numpy()
+    assert logit_err(y, model_golden["res8/hardened/logits"]) <= LOGIT_TOL
+
+
+def test_wave_to_logits_is_frontend_then_model(dev):
+    ap = AudioProcessor()
+    m, _ = gpu_model("res8", "hardened", dev)
+    w = torch.from_numpy(synth.speechlike(6, seed=4)).to(dev)
+    with torch.no_grad():
+        a = m.forward_wave(w, ap)
+        b = m(ap.compute_mfccs_batch(w))
+    assert torch.equal(a, b)
+
+
+def test_acc_kernel(dev):
+    from honk2_b200.metric import Acc
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(1000, 12, generator=g)
+    logits[5, 3] = logits[5, 7] = 9.0   # tie -> lowest index, like torch.argmax
+    target = torch.randint(0, 12, (1000,), generator=g)
+    acc = Acc()
+    pred = acc.accumulate(logits.to(dev), target.to(dev), return_pred=True)
+    acc.accumulate(logits[:10].to(dev), target[:10].to(dev))
+    c1, t1 = model_ref.acc_counts(logits, target)
+    c2, t2 = model_ref.acc_counts(logits[:10], target[:10])
+    assert acc.counts() == (c1 + c2, t1 + t2)
+    assert torch.equal(pred.cpu(), torch.argmax(logits, 1))
+
+
+@pytest.mark.parametrize("name", ["res15"])
+def test_fp32_full_batch_properties(dev, name):
+    """BASELINE size (B = 8192 is scaled to 1024 for the fp32 CUDA-core path to keep the suite
+    short): batch-split invariance and agreement with the oracle on sampled rows."""
+    kind, cfg = model_config(name)
+    m, sd = gpu_model(name, "hardened", dev)
+    ap = AudioProcessor()
+    w = synth.broadband(1024, seed=8)
+    wd = torch.from_numpy(w).to(dev)
+    with torch.no_grad():
+        y = m.forward_wave(wd, ap)
+        y2 = torch.cat([m.forward_wave(wd[:300], ap), m.forward_wave(wd[300:], ap)])
+    assert torch.equal(y, y2)
+    idx = np.random.default_rng(1).choice(1024, 8, replace=False)
+    ref = model_ref.forward(kind, sd, cfg, torch.from_numpy(mfcc_ref.compute_mfccs_batch(w[idx]))).numpy()
+    got = y[torch.from_numpy(idx).to(dev)].cpu().numpy()
+    assert logit_err(got, ref) <= LOGIT_TOL
+    assert np.array_equal(got.argmax(1), ref.argmax(1))

@@ -1,0 +1,97 @@
+"""Pins oracle/mfcc_ref.py (the numpy restatement of AudioProcessor.compute_mfccs,
+/root/reference/utils/audio_processor.py:18-30): committed goldens, the degenerate-DCT identity,
+an independent torchaudio cross-check, and the edge semantics the reference has."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import scaled_err
+from oracle import mfcc_ref
+
+
+def test_waves_regenerate_bit_exact(golden_waves, mfcc_golden):
+    for name, w in golden_waves.items():
+        sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(w).tobytes()).digest(), np.uint8)
+        assert np.array_equal(sha, mfcc_golden[f"{name}_sha"]), f"synthetic generator drifted for {name}"
+
+
+def test_oracle_matches_golden(golden_waves, mfcc_golden):
+    for name, w in golden_waves.items():
+        got = mfcc_ref.compute_mfccs_batch(w)
+        ref = mfcc_golden[f"{name}_feat"]
+        assert got.shape == ref.shape and got.dtype == np.float32
+        assert scaled_err(got, ref) <= 2e-6, name
+
+
+def test_shape_and_layout():
+    y = np.random.default_rng(0).standard_normal(16000).astype(np.float32)
+    f = mfcc_ref.compute_mfccs(y)
+    assert f.shape == (101, 40, 1) and f.dtype == np.float32      # audio_processor.py:29
+    assert mfcc_ref.compute_mfccs(y[:12345]).shape == (1 + 12345 // 160, 40, 1)
+    assert mfcc_ref.compute_mfccs(np.zeros(144000)).shape == (901, 40, 1)  # hey_snips 9 s
+
+
+def test_dct_of_length_one_axis_is_times_two():
+    """audio_processor.py:28 -- scipy.fftpack.dct over the length-1 last axis == 2*x."""
+    fftpack = pytest.importorskip("scipy.fftpack")
+    x = np.random.default_rng(1).standard_normal((40, 1)).astype(np.float32)
+    assert np.allclose(fftpack.dct(x), 2 * x)
+    y = 0.1 * np.random.default_rng(2).standard_normal(4000).astype(np.float32)
+    data = mfcc_ref.mel_power(y)
+    pos = data > 0
+    data[pos] = np.log(data[pos])
+    cols = [fftpack.dct(c) for c in np.split(data, data.shape[1], axis=1)]      # :28
+    ref = np.array(cols, order="F").astype(np.float32)                            # :29
+    assert np.array_equal(ref, mfcc_ref.compute_mfccs(y))
+
+
+def test_zero_input_gives_exact_zero_features():
+    f = mfcc_ref.compute_mfccs(np.zeros(16000, dtype=np.float64))   # silence clip, gsc_dataset.py:166
+    assert np.all(f == 0.0)
+
+
+def test_float64_input_matches_float32_path():
+    y = (0.1 * np.random.default_rng(3).standard_normal(16000))
+    a = mfcc_ref.compute_mfccs(y)
+    b = mfcc_ref.compute_mfccs(y.astype(np.float32))
+    assert scaled_err(a, b) < 1e-4
+
+
+def test_valid_audio_errors():
+    with pytest.raises(ValueError):
+        mfcc_ref.compute_mfccs(np.zeros(16000, dtype=np.int16))
+    bad = np.zeros(16000, dtype=np.float32)
+    bad[5] = np.nan
+    with pytest.raises(ValueError):
+        mfcc_ref.compute_mfccs(bad)
+    with pytest.raises(ValueError):
+        mfcc_ref.compute_mfccs(np.zeros((2, 16000), dtype=np.float32))
+
+
+def test_filterbank_facts():
+    """230 non-zeros on FFT bins 1..119, no empty filter."""
+    W = mfcc_ref.mel_filterbank()
+    assert W.shape == (40, 241) and W.dtype == np.float32
+    assert int((W != 0).sum()) == 230
+    cols = np.nonzero(W.any(axis=0))[0]
+    assert cols.min() == 1 and cols.max() == 119
+    assert (W != 0).sum(axis=1).min() >= 3
+
+
+def test_against_torchaudio(golden_waves):
+    """Independent implementation of the same published algorithm (Slaney mel, reflect pad,
+    periodic Hann, power 2)."""
+    torchaudio = pytest.importorskip("torchaudio")
+    import torch
+    mel = torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=480, hop_length=160, f_min=20.0,
+                                               f_max=4000.0, n_mels=40, power=2.0, center=True, pad_mode="reflect",
+                                               norm="slaney", mel_scale="slaney")
+    for name in ("broadband", "noisy", "speechlike"):
+        w = golden_waves[name].astype(np.float32)
+        ours = mfcc_ref.compute_mfccs_batch(w)
+        ta = (2.0 * torch.log(mel(torch.from_numpy(w)))).transpose(1, 2).numpy()
+        live = ours != 0
+        assert scaled_err(ta[live], ours[live]) < 1e-4, name
+    fb = torchaudio.functional.melscale_fbanks(241, 20.0, 4000.0, 40, 16000, norm="slaney", mel_scale="slaney")
+    assert np.abs(fb.numpy().T - mfcc_ref.mel_filterbank()).max() < 1e-6
