@@ -1,13 +1,757 @@
-// placeholder until the tcgen05 path lands (replaced in the next commit)
+// bf16 tensor-core ResNet path for sm_100a: tcgen05.mma (UMMA) implicit-GEMM 3x3 dilated
+// convolution with TMA-staged halo tiles, TMEM accumulators and a fused
+// ReLU / residual / BatchNorm epilogue (/root/reference/model/resnet.py:48-55), plus the
+// conv_0 and mean+linear kernels for the same activation layout.
+//
+// Activation layout ("planar-8"): [B][NP][H][W][8] bf16, NP = CP/8 planes of 8 channels,
+// CP = channels padded to a multiple of 16 (45 -> 48).  One plane row is W*16 contiguous bytes,
+// so a TMA box {8 ch, Wp, rows} lands in shared memory as a dense array of 16-byte "positions":
+// exactly the UMMA K-major SWIZZLE_NONE canonical layout (core matrix = 8 positions x 16 B,
+// SBO = 128 B), in which a pixel shift is nothing but a start-address offset.
+//
+// Implicit GEMM per tap (dh, dw) and 16-channel chunk kc:
+//   D[128 positions x CP] += A[128 positions x 16] (shifted view of the staged tile)
+//                          * B[16 x CP]            (weights, resident in shared memory)
+// Positions are flat indices p = r * Wp + c into the zero-padded tile rows (Wp = W + d: the d
+// left-pad columns of row r+1 double as the right padding of row r; TMA out-of-bounds fill
+// supplies every zero).  Outputs at pad positions are computed and discarded.
+//
+// Warp roles (192 threads, 1 CTA per SM, persistent over tiles):
+//   warp 0     TMA producer: one stage = one 16-channel chunk of the haloed input tile
+//   warp 1     MMA issuer (one elected lane) + TMEM allocation
+//   warps 2-5  epilogue: tcgen05.ld -> ReLU -> +skip -> BN -> bf16 planar-8 stores
+// TMEM holds two accumulator buffers (up to 5 M-tiles x CP columns each) so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
 #include "tc.cuh"
+#include <cuda.h>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <vector>
+
 namespace kws {
-struct TcResNet { kws_resnet_config cfg; };
-int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) { *out = new TcResNet{cfg}; return KWS_OK; }
-void tc_resnet_destroy(TcResNet* p) { delete p; }
-int tc_resnet_set_weights(TcResNet*, const kws_resnet_weights&, float* const*, float* const*, cudaStream_t) { return KWS_OK; }
-size_t tc_resnet_workspace_bytes(const TcResNet*, int64_t, int, int, int) { return 0; }
-int tc_resnet_forward(TcResNet*, const float*, int64_t, int, int, float*, void*, size_t, int, LaunchProfiler*, cudaStream_t) {
-  set_error("bf16 tensor-core path is not built in this revision");
-  return KWS_ERR_UNSUPPORTED;
+
+constexpr int kTcThreads = 192;
+constexpr int kAccCols = 256;     // TMEM columns per accumulator buffer
+constexpr int kMaxStages = 8;
+constexpr long long kSpinLimitCycles = 4000000000ll;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kSpinLimitCycles) __trap();   // ~2 s: far beyond any legitimate wait
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// [0,14) addr>>4, [16,30) LBO>>4 (byte distance between the two 8-element K halves),
+// [32,46) SBO>>4 (byte distance between 8-row groups), [46,48) version = 1, [61,64) layout = 0.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor: c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1, K-major both,
+// n>>3 at [17,23), m>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TcGeom {
+  int H, W, d, dpad, Wp, R, tiles_per_utt;
+  int rows_box, n_boxes, box_stride;   // bytes between row-block boxes inside a slab
+  int h_start[3];                      // first input row of box bx relative to the tile's h0
+  int tap_off[3];                      // byte offset inside a slab of tap row dh = -1, 0, +1
+  int slab_bytes, stage_bytes, n_stages, side_taps;
+  int smem_w_off, smem_ring_off, smem_total;
+};
+
+struct TcConvParams {
+  const __nv_bfloat16* wpack;  // [9][NKC][2][CP][8]
+  const float* bn_scale;       // [CP] (0 for pad channels)
+  const float* bn_shift;       // [CP]
+  const __nv_bfloat16* prev_in;
+  __nv_bfloat16* prev_out;
+  __nv_bfloat16* y;
+  int B, total_tiles;
+  TcGeom g;
+};
+
+template <int NKC>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p) {
+  constexpr int CP = 16 * NKC;       // padded channels = UMMA N
+  constexpr int NP = 2 * NKC;        // 8-channel planes
+  constexpr int W_HALF = CP * 16;    // bytes of one [CP][8] weight half-slab
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const TcGeom& g = p.g;
+
+  // ---- shared memory carve-up
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);            // full[8], empty[8], tfull[2], tempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 20);
+  float* s_scale = reinterpret_cast<float*>(smem + 256);          // [CP]
+  float* s_shift = s_scale + CP;                                  // [CP]
+  unsigned char* s_w = smem + g.smem_w_off;
+  unsigned char* s_ring = smem + g.smem_ring_off;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmap);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wpack);
+    uint4* dst = reinterpret_cast<uint4*>(s_w);
+    for (int i = threadIdx.x; i < 9 * NKC * 2 * CP; i += kTcThreads) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < CP; i += kTcThreads) { s_scale[i] = p.bn_scale[i]; s_shift[i] = p.bn_shift[i]; }
+    fence_async_smem();   // generic-proxy writes -> visible to the async proxy (UMMA reads s_w)
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_utt = g.tiles_per_utt;
+  auto tile_rows = [&](int tix) { return min(g.R, g.H - tix * g.R); };
+  auto tile_mt = [&](int tix) { return (tile_rows(tix) * g.Wp + 127) >> 7; };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)(2 * g.n_boxes * g.rows_box * g.Wp * 16);
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int b = t / tiles_per_utt, tix = t - b * tiles_per_utt;
+        const int h0 = tix * g.R;
+        for (int kc = 0; kc < NKC; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), tx);
+          const uint32_t sbase = smem_u32(s_ring + (size_t)stage * g.stage_bytes);
+          for (int half = 0; half < 2; ++half)
+            for (int bx = 0; bx < g.n_boxes; ++bx)
+              tma_load_4d(sbase + half * g.slab_bytes + bx * g.box_stride, &tmap, full_bar(stage), 0, -g.dpad,
+                          h0 + g.h_start[bx], b * NP + 2 * kc + half);
+          if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    constexpr uint32_t idesc = umma_idesc(128, CP);
+    const uint32_t w_base = smem_u32(s_w);
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int tix = t % tiles_per_utt;
+      const int n_mt = tile_mt(tix);
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      for (int kc = 0; kc < NKC; ++kc) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sbase = smem_u32(s_ring + (size_t)stage * g.stage_bytes);
+          bool first = (kc == 0);
+          for (int dh = 0; dh < 3; ++dh) {
+            for (int dw = 0; dw < 3; ++dw) {
+              if (dw != 1 && !g.side_taps) continue;
+              const uint32_t a0 = sbase + g.tap_off[dh] + (dw - 1) * g.d * 16;
+              const uint64_t bdesc =
+                  umma_desc(w_base + (((dh * 3 + dw) * NKC + kc) * 2) * W_HALF, W_HALF, 128);
+              for (int mt = 0; mt < n_mt; ++mt) {
+                const uint64_t adesc = umma_desc(a0 + mt * 2048, g.slab_bytes, 128);
+                umma_f16(tmem_base + acc * kAccCols + mt * CP, adesc, bdesc, idesc, first ? 0u : 1u);
+              }
+              first = false;
+            }
+          }
+          umma_commit(empty_bar(stage));                       // stage reusable once these MMAs retire
+          if (kc == NKC - 1) umma_commit(tfull_bar(acc));      // accumulators complete
+        }
+        __syncwarp();
+        if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int q = warp & 3;   // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool has_prev = p.prev_in != nullptr;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int b = t / tiles_per_utt, tix = t - b * tiles_per_utt;
+      const int h0 = tix * g.R;
+      const int rows = tile_rows(tix);
+      const int n_mt = tile_mt(tix);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      for (int mt = 0; mt < n_mt; ++mt) {
+        const int pos = mt * 128 + q * 32 + lane;
+        const int r = pos / g.Wp;
+        const int w = pos - r * g.Wp - g.dpad;
+        const bool valid = (w >= 0) && (r < rows);
+        const int64_t pix = ((int64_t)(h0 + r) * g.W + w);
+        const int64_t plane_stride = (int64_t)g.H * g.W;   // in 8-channel units
+        const int64_t base = ((int64_t)b * NP) * plane_stride + pix;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP;
+#pragma unroll
+        for (int j = 0; j < NKC; ++j) {
+          uint32_t v[16];
+          tmem_ld16(taddr + 16 * j, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const int64_t off = base + (int64_t)(2 * j + hf) * plane_stride;   // uint4 units
+              float x[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[8 * hf + e]), 0.f);
+              if (has_prev) {
+                const uint4 pv = __ldg(reinterpret_cast<const uint4*>(p.prev_in) + off);
+                const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(pb[e]);
+                  x[2 * e] += f.x;
+                  x[2 * e + 1] += f.y;
+                }
+                uint4 po;
+                __nv_bfloat162* pob = reinterpret_cast<__nv_bfloat162*>(&po);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pob[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+                reinterpret_cast<uint4*>(p.prev_out)[off] = po;
+              }
+              uint4 yo;
+              __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = 16 * j + 8 * hf + 2 * e;
+                yb[e] = __floats2bfloat162_rn(fmaf(x[2 * e], s_scale[c], s_shift[c]),
+                                              fmaf(x[2 * e + 1], s_scale[c + 1], s_shift[c + 1]));
+              }
+              reinterpret_cast<uint4*>(p.y)[off] = yo;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv_0 (1 -> C, 3x3, pad 1) + ReLU + AvgPool -> planar-8 bf16 (resnet.py:40-44).
+// One thread per output pixel; channels in groups of 8 -> one 16-byte store per plane.
+__global__ void __launch_bounds__(256)
+conv0_p8_kernel(const float* __restrict__ feat, const float* __restrict__ w0, __nv_bfloat16* __restrict__ out,
+                int T, int F, int C, int NP, int ph, int pw, int Ho, int Wo, int rows_per_tile) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int in_rows = rows_per_tile * ph + 2, in_cols = F + 2;
+  float* s_in = smem_f;
+  float* s_w = smem_f + round_up(in_rows * in_cols, 4);   // [NP*8][12], zero for pad channels
+  const int64_t b = blockIdx.y;
+  const int ho0 = blockIdx.x * rows_per_tile;
+  const float* src = feat + b * (int64_t)T * F;
+  for (int i = threadIdx.x; i < in_rows * in_cols; i += blockDim.x) {
+    const int r = i / in_cols, c = i - r * in_cols;
+    const int h = ho0 * ph - 1 + r, w = c - 1;
+    s_in[i] = (h >= 0 && h < T && w >= 0 && w < F) ? __ldg(src + (int64_t)h * F + w) : 0.f;
+  }
+  for (int i = threadIdx.x; i < NP * 8 * 12; i += blockDim.x) {
+    const int c = i / 12, k = i - c * 12;
+    s_w[i] = (k < 9 && c < C) ? __ldg(w0 + c * 9 + k) : 0.f;
+  }
+  __syncthreads();
+  const int r = threadIdx.x / Wo, wo = threadIdx.x - r * Wo;
+  const int ho = ho0 + r;
+  if (r >= rows_per_tile || ho >= Ho) return;
+  const float inv = 1.f / (float)(ph * pw);
+  const int64_t plane_stride = (int64_t)Ho * Wo;
+  uint4* dst = reinterpret_cast<uint4*>(out) + (b * NP) * plane_stride + (int64_t)ho * Wo + wo;
+  for (int pl = 0; pl < NP; ++pl) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int i = 0; i < ph; ++i)
+      for (int j = 0; j < pw; ++j) {
+        const float* q = s_in + (r * ph + i) * in_cols + wo * pw + j;
+        float xin[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int e = 0; e < 3; ++e) xin[a * 3 + e] = q[a * in_cols + e];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float* wc = s_w + (pl * 8 + e) * 12;
+          const float4 wa = *reinterpret_cast<const float4*>(wc);
+          const float4 wb = *reinterpret_cast<const float4*>(wc + 4);
+          float v = xin[0] * wa.x;
+          v = fmaf(xin[1], wa.y, v); v = fmaf(xin[2], wa.z, v); v = fmaf(xin[3], wa.w, v);
+          v = fmaf(xin[4], wb.x, v); v = fmaf(xin[5], wb.y, v); v = fmaf(xin[6], wb.z, v);
+          v = fmaf(xin[7], wb.w, v); v = fmaf(xin[8], wc[8], v);
+          acc[e] += fmaxf(v, 0.f);
+        }
+      }
+    uint4 o;
+    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(acc[2 * e] * inv, acc[2 * e + 1] * inv);
+    dst[pl * plane_stride] = o;
+  }
+}
+
+// mean over H*W of planar-8 bf16 + Linear (resnet.py:57-59).  One CTA per utterance.
+__global__ void __launch_bounds__(256)
+tail_p8_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ out_w, const float* __restrict__ out_b,
+               float* __restrict__ logits, int C, int NP, int HW, int n_labels) {
+  __shared__ float s_part[8][64];
+  __shared__ float s_mean[64];
+  const int64_t b = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int pl = 0; pl < NP; ++pl) {
+    const uint4* src = reinterpret_cast<const uint4*>(y) + (b * NP + pl) * (int64_t)HW;
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    for (int i = threadIdx.x; i < HW; i += 256) {
+      const uint4 v = __ldg(src + i);
+      const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(vb[e]);
+        s[2 * e] += f.x;
+        s[2 * e + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s[e] += __shfl_xor_sync(0xffffffffu, s[e], o);
+      if (lane == 0) s_part[warp][pl * 8 + e] = s[e];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < NP * 8) {
+    float t = 0.f;
+    for (int wv = 0; wv < 8; ++wv) t += s_part[wv][threadIdx.x];
+    s_mean[threadIdx.x] = t / (float)HW;
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < n_labels; l += 256) {
+    float v = __ldg(out_b + l);
+    for (int c = 0; c < C; ++c) v = fmaf(s_mean[c], __ldg(out_w + l * C + c), v);
+    logits[b * n_labels + l] = v;
+  }
+}
+
+// torch [C][C][3][3] fp32 -> [9][NKC][2][CP][8] bf16 (tap, 16-ch chunk, K half, cout, 8 cin)
+__global__ void pack_conv3x3_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int NKC) {
+  const int CP = 16 * NKC;
+  const int total = 9 * NKC * 2 * CP * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7;
+    int t = i >> 3;
+    const int co = t % CP; t /= CP;
+    const int half = t & 1; t >>= 1;
+    const int kc = t % NKC;
+    const int tap = t / NKC;
+    const int ci = kc * 16 + half * 8 + e;
+    const float v = (co < C && ci < C) ? w[((int64_t)co * C + ci) * 9 + tap] : 0.f;
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void pad_bn_kernel(const float* __restrict__ scale, const float* __restrict__ shift,
+                              float* __restrict__ scale_p, float* __restrict__ shift_p, int C, int CP) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < CP) {
+    scale_p[c] = c < C ? scale[c] : 0.f;
+    shift_p[c] = c < C ? shift[c] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+struct TcResNet {
+  kws_resnet_config cfg{};
+  int NKC = 0, CP = 0, NP = 0;
+  bool supported = false;
+  int n_sms = 148;
+  void* blob = nullptr;
+  std::vector<__nv_bfloat16*> wpack;        // per layer
+  std::vector<float*> scale_p, shift_p;     // per layer, padded to CP
+  float* conv0_w = nullptr;                 // [C][9]
+  float* out_w = nullptr;
+  float* out_b = nullptr;
+  std::map<std::tuple<const void*, int64_t, int, int, int>, CUtensorMap> maps;
+};
+
+static int tc_max_mt(int CP) { return std::min(8, kAccCols / CP); }
+
+// Tile geometry of one layer launch.  Returns false if the layer cannot be tiled.
+static bool tc_geom(int NKC, int H, int W, int d, TcGeom* g) {
+  const int CP = 16 * NKC;
+  g->H = H; g->W = W; g->d = d;
+  g->side_taps = d < W ? 1 : 0;
+  g->dpad = g->side_taps ? d : 0;
+  g->Wp = W + g->dpad;
+  if (g->Wp > 256) return false;
+  const int max_pos = tc_max_mt(CP) * 128;
+  const int Rmax = std::min(H, max_pos / g->Wp);
+  if (Rmax < 1) return false;
+  const int w_bytes = 9 * NKC * 2 * CP * 16;
+  g->smem_w_off = 256 + round_up(2 * CP * 4, 128);
+  g->smem_ring_off = round_up(g->smem_w_off + w_bytes, 1024);
+  const int budget = 227 * 1024 - g->smem_ring_off - 4096;
+  // pick the rows-per-tile that issues the fewest 128-position M-tiles per utterance
+  // (ties: fewer tiles), among those whose staged input fits shared memory with >= 2 stages
+  int best_R = 0, best_mt = 1 << 30, best_stages = 0;
+  for (int R = Rmax; R >= 1; --R) {
+    const int full = H / R, rem = H - full * R;
+    const int mt = full * ceil_div(R * g->Wp, 128) + ceil_div(rem * g->Wp, 128);
+    if (mt >= best_mt) continue;
+    const bool dense = d <= R;
+    const int rows_box = dense ? R + 2 * d + 1 : R + 1;
+    if (rows_box > 256) continue;
+    const int slab = (dense ? 1 : 3) * round_up(rows_box * g->Wp * 16, 128);
+    if (slab >= (1 << 18)) continue;
+    const int stages = std::min(kMaxStages, budget / (2 * slab));
+    if (stages < 2) continue;
+    best_R = R; best_mt = mt; best_stages = stages;
+  }
+  if (best_R == 0) return false;
+  const int R = best_R;
+  const bool dense = d <= R;
+  g->R = R;
+  g->tiles_per_utt = ceil_div(H, R);
+  g->n_boxes = dense ? 1 : 3;
+  g->rows_box = dense ? R + 2 * d + 1 : R + 1;
+  g->box_stride = round_up(g->rows_box * g->Wp * 16, 128);
+  g->slab_bytes = g->n_boxes * g->box_stride;
+  g->stage_bytes = 2 * g->slab_bytes;
+  for (int k = 0; k < 3; ++k) {
+    g->h_start[k] = dense ? -d : (k - 1) * d;
+    g->tap_off[k] = dense ? k * d * g->Wp * 16 : k * g->box_stride;
+  }
+  g->n_stages = best_stages;
+  g->smem_total = g->smem_ring_off + best_stages * g->stage_bytes + 4096;
+  if (g->smem_total < 120 * 1024) g->smem_total = 120 * 1024;   // one CTA per SM (it owns all 512 TMEM columns)
+  return true;
+}
+
+int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
+  TcResNet* p = new TcResNet();
+  p->cfg = cfg;
+  const int C = cfg.n_maps;
+  p->NKC = ceil_div(C, 16);
+  p->CP = 16 * p->NKC;
+  p->NP = 2 * p->NKC;
+  p->supported = p->NKC >= 1 && p->NKC <= 4 && get_encode_fn() != nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&p->n_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (p->supported) {
+    const int n = cfg.n_layers;
+    const size_t w_bytes = round_up<size_t>((size_t)9 * p->NKC * 2 * p->CP * 16, 256);
+    const size_t v_bytes = round_up<size_t>(p->CP * sizeof(float), 256);
+    const size_t total = n * (w_bytes + 2 * v_bytes) + round_up<size_t>(C * 9 * 4, 256) +
+                         round_up<size_t>((size_t)cfg.n_labels * C * 4, 256) + round_up<size_t>(cfg.n_labels * 4, 256);
+    if (cudaMalloc(&p->blob, total) != cudaSuccess) {
+      set_error("tc_resnet_create: cudaMalloc(%zu) failed", total);
+      delete p;
+      return KWS_ERR_CUDA;
+    }
+    char* b = static_cast<char*>(p->blob);
+    for (int i = 0; i < n; ++i) {
+      p->wpack.push_back(reinterpret_cast<__nv_bfloat16*>(b)); b += w_bytes;
+      p->scale_p.push_back(reinterpret_cast<float*>(b)); b += v_bytes;
+      p->shift_p.push_back(reinterpret_cast<float*>(b)); b += v_bytes;
+    }
+    p->conv0_w = reinterpret_cast<float*>(b); b += round_up<size_t>(C * 9 * 4, 256);
+    p->out_w = reinterpret_cast<float*>(b); b += round_up<size_t>((size_t)cfg.n_labels * C * 4, 256);
+    p->out_b = reinterpret_cast<float*>(b);
+  }
+  *out = p;
+  return KWS_OK;
+}
+
+void tc_resnet_destroy(TcResNet* p) {
+  if (!p) return;
+  if (p->blob) cudaFree(p->blob);
+  delete p;
+}
+
+int tc_resnet_set_weights(TcResNet* p, const kws_resnet_weights& w, float* const* bn_scale, float* const* bn_shift,
+                          cudaStream_t st) {
+  if (!p->supported) return KWS_OK;
+  const int C = p->cfg.n_maps, n = p->cfg.n_layers, L = p->cfg.n_labels;
+  for (int i = 0; i < n; ++i) {
+    pack_conv3x3_tc_kernel<<<ceil_div(9 * p->NKC * 2 * p->CP * 8, 256), 256, 0, st>>>(w.conv_w[i], p->wpack[i], C, p->NKC);
+    KWS_CUDA(cudaGetLastError());
+    pad_bn_kernel<<<1, 64, 0, st>>>(bn_scale[i], bn_shift[i], p->scale_p[i], p->shift_p[i], C, p->CP);
+    KWS_CUDA(cudaGetLastError());
+  }
+  KWS_CUDA(cudaMemcpyAsync(p->conv0_w, w.conv0_w, sizeof(float) * C * 9, cudaMemcpyDeviceToDevice, st));
+  KWS_CUDA(cudaMemcpyAsync(p->out_w, w.out_w, sizeof(float) * L * C, cudaMemcpyDeviceToDevice, st));
+  KWS_CUDA(cudaMemcpyAsync(p->out_b, w.out_b, sizeof(float) * L, cudaMemcpyDeviceToDevice, st));
+  return KWS_OK;
+}
+
+static void tc_map_hw(const kws_resnet_config& c, int T, int F, int* H, int* W) {
+  const int ph = c.pool_h > 0 ? c.pool_h : 1, pw = c.pool_w > 0 ? c.pool_w : 1;
+  *H = T / ph;
+  *W = F / pw;
+}
+
+static int64_t tc_chunk(const TcResNet* p, int64_t B, int H, int W, int chunk) {
+  const int64_t per = (int64_t)p->NP * H * W * 16;
+  int64_t c = chunk > 0 ? chunk : (100ll << 20) / (3 * std::max<int64_t>(per, 1));
+  if (chunk <= 0) {
+    // whole number of CTA waves for the common 7-tile geometry is not knowable here; keep it simple
+    if (c < 16) c = 16;
+    if (c > 2048) c = 2048;
+  }
+  if (c > B) c = B;
+  if (c < 1) c = 1;
+  return c;
+}
+
+static bool tc_layers_ok(const TcResNet* p, int H, int W) {
+  TcGeom g;
+  for (int i = 1; i <= p->cfg.n_layers; ++i) {
+    const int d = p->cfg.use_dilation ? (1 << ((i - 1) / 3)) : 1;
+    if (!tc_geom(p->NKC, H, W, d, &g)) return false;
+  }
+  return true;
+}
+
+size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int chunk) {
+  if (!p || !p->supported) return 0;
+  int H, W;
+  tc_map_hw(p->cfg, T, F, &H, &W);
+  if (H < 1 || W < 1 || W > 256 || !tc_layers_ok(p, H, W)) return 0;
+  const int64_t c = tc_chunk(p, B, H, W, chunk);
+  return 3 * round_up<size_t>((size_t)c * p->NP * H * W * 16, 1024);
+}
+
+static int tc_get_map(TcResNet* p, const void* base, int64_t planes, int H, int W, const TcGeom& g, CUtensorMap** out) {
+  auto key = std::make_tuple(base, planes, H, W, g.d * 1024 + g.rows_box);
+  auto it = p->maps.find(key);
+  if (it == p->maps.end()) {
+    if (p->maps.size() > 256) p->maps.clear();
+    CUtensorMap m;
+    const cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+    const cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+    const cuuint32_t box[4] = {8, (cuuint32_t)g.Wp, (cuuint32_t)g.rows_box, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed (%d) for W=%d H=%d planes=%lld box=%dx%d", (int)r, W, H,
+                (long long)planes, g.Wp, g.rows_box);
+      return KWS_ERR_CUDA;
+    }
+    it = p->maps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return KWS_OK;
+}
+
+template <int NKC>
+static int tc_launch_conv(const CUtensorMap& map, const TcConvParams& prm, int grid, cudaStream_t st) {
+  KWS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NKC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                prm.g.smem_total));
+  conv3x3_tc_kernel<NKC><<<grid, kTcThreads, prm.g.smem_total, st>>>(map, prm);
+  KWS_CHECK_LAUNCH();
+  return KWS_OK;
+}
+
+int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, float* logits, void* ws,
+                      size_t ws_bytes, int chunk_cfg, LaunchProfiler* prof, cudaStream_t st) {
+  if (!p->supported) {
+    set_error("bf16 tensor-core path supports 1..64 feature maps (got %d) and needs cuTensorMapEncodeTiled",
+              p->cfg.n_maps);
+    return KWS_ERR_UNSUPPORTED;
+  }
+  const kws_resnet_config& c = p->cfg;
+  int H, W;
+  tc_map_hw(c, T, F, &H, &W);
+  KWS_REQUIRE(H >= 1 && W >= 1, "ResNet: input %dx%d is smaller than the pooling window", T, F);
+  const size_t need = tc_resnet_workspace_bytes(p, B, T, F, chunk_cfg);
+  if (need == 0) {
+    set_error("bf16 tensor-core path cannot tile a %dx%d map", H, W);
+    return KWS_ERR_UNSUPPORTED;
+  }
+  if (ws == nullptr || ws_bytes < need) {
+    set_error("ResNet bf16 forward needs %zu bytes of workspace, got %zu", need, ws_bytes);
+    return KWS_ERR_WORKSPACE;
+  }
+  const int64_t chunk = tc_chunk(p, B, H, W, chunk_cfg);
+  const size_t buf = round_up<size_t>((size_t)chunk * p->NP * H * W * 16, 1024);
+  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws));
+  __nv_bfloat16* A[2] = {reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + buf),
+                         reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + 2 * buf)};
+  const int ph = c.pool_h > 0 ? c.pool_h : 1, pw = c.pool_w > 0 ? c.pool_w : 1;
+  KWS_REQUIRE(W <= 256, "conv_0: map width %d exceeds 256", W);
+  const int rows0 = std::max(1, std::min(H, 256 / W));
+  const size_t smem0 = sizeof(float) * (round_up((rows0 * ph + 2) * (F + 2), 4) + p->NP * 8 * 12);
+  KWS_REQUIRE(smem0 <= 48 * 1024, "conv_0: tile needs %zu bytes of shared memory", smem0);
+
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    const int64_t nb = std::min(chunk, B - b0);
+    if (prof) prof->tick(1, st);
+    conv0_p8_kernel<<<dim3(ceil_div(H, rows0), (unsigned)nb), 256, smem0, st>>>(
+        feat + b0 * (int64_t)T * F, p->conv0_w, P, T, F, c.n_maps, p->NP, ph, pw, H, W, rows0);
+    KWS_CHECK_LAUNCH();
+    const __nv_bfloat16* x = P;
+    int flip = 0;
+    for (int i = 1; i <= c.n_layers; ++i) {
+      TcConvParams prm;
+      const int d = c.use_dilation ? (1 << ((i - 1) / 3)) : 1;
+      KWS_REQUIRE(tc_geom(p->NKC, H, W, d, &prm.g), "bf16 conv: cannot tile H=%d W=%d d=%d", H, W, d);
+      CUtensorMap* map = nullptr;
+      KWS_TRY(tc_get_map(p, x, nb * p->NP, H, W, prm.g, &map));
+      prm.wpack = p->wpack[i - 1];
+      prm.bn_scale = p->scale_p[i - 1];
+      prm.bn_shift = p->shift_p[i - 1];
+      prm.prev_in = (i % 2 == 0) ? P : nullptr;
+      prm.prev_out = (i % 2 == 0) ? P : nullptr;
+      prm.y = A[flip];
+      prm.B = (int)nb;
+      prm.total_tiles = (int)nb * prm.g.tiles_per_utt;
+      const int grid = std::min(p->n_sms, prm.total_tiles);
+      if (prof) prof->tick(0, st);
+      switch (p->NKC) {
+        case 1: KWS_TRY(tc_launch_conv<1>(*map, prm, grid, st)); break;
+        case 2: KWS_TRY(tc_launch_conv<2>(*map, prm, grid, st)); break;
+        case 3: KWS_TRY(tc_launch_conv<3>(*map, prm, grid, st)); break;
+        default: KWS_TRY(tc_launch_conv<4>(*map, prm, grid, st)); break;
+      }
+      x = A[flip];
+      flip ^= 1;
+    }
+    if (prof) prof->tick(1, st);
+    tail_p8_kernel<<<(unsigned)nb, 256, 0, st>>>(x, p->out_w, p->out_b, logits + b0 * c.n_labels, c.n_maps, p->NP,
+                                                 H * W, c.n_labels);
+    KWS_CHECK_LAUNCH();
+  }
+  return KWS_OK;
+}
+
 }  // namespace kws

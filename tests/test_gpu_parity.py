@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import honk2_b200
-from conftest import logit_err, scaled_err
+from conftest import logit_err, mfcc_err, scaled_err
 from honk2_b200 import AudioProcessor, synth
 from honk2_b200.zoo import MODEL_ZOO, model_config
 from oracle import mfcc_ref, model_ref
@@ -44,7 +44,12 @@ def test_mfcc_matches_golden_and_oracle(dev, golden_waves, mfcc_golden):
         got = ap.compute_mfccs_batch(torch.from_numpy(w.astype(np.float32)).to(dev)).cpu().numpy()
         ref = mfcc_golden[f"{name}_feat"]
         assert got.shape == ref.shape
-        assert scaled_err(got, ref) <= MFCC_TOL, (name, scaled_err(got, ref))
+        err, n_floor, floor_ok = mfcc_err(got, ref)
+        assert err <= MFCC_TOL, (name, err)
+        assert floor_ok, f"{name}: numerical-floor bins are not floor bins in the CUDA output"
+        if name != "edge":   # only the exactly periodic edge vectors have numerical-floor bins
+            assert n_floor == 0, (name, n_floor)
+            assert scaled_err(got, ref) <= MFCC_TOL
 
 
 def test_mfcc_reference_api(dev, golden_waves):

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import honk2_b200  # noqa: E402
-from conftest import logit_err, scaled_err  # noqa: E402
+from conftest import logit_err, mfcc_err, scaled_err  # noqa: E402
 from honk2_b200 import AudioProcessor, find_cls, synth  # noqa: E402
 from honk2_b200.zoo import MODEL_ZOO, model_config  # noqa: E402
 from oracle import mfcc_ref, model_ref  # noqa: E402
@@ -44,7 +44,8 @@ def main():
             ref = gold[f"{name}_feat"]
             e = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
             worst = np.unravel_index(np.argmax(e), e.shape)
-            return f"scaled err max {e.max():.3e} mean {e.mean():.3e} worst@{worst} got {got[worst]:.5f} ref {ref[worst]:.5f}"
+            fe_err, n_floor, floor_ok = mfcc_err(got, ref)
+            return f"resolved err {fe_err:.3e} floor bins {n_floor} ok={floor_ok} | raw scaled err max {e.max():.3e} mean {e.mean():.3e} worst@{worst} got {got[worst]:.5f} ref {ref[worst]:.5f}"
         check(f"mfcc {name}", f)
 
     feats = torch.from_numpy(mfcc_ref.compute_mfccs_batch(synth.noisy_dataset_like(5, seed=9)))
