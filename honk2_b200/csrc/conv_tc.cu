@@ -31,7 +31,9 @@
 
 namespace kws {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcThreads = 32 * (2 + kTcEpiWarps);   // warp 0 TMA, warp 1 MMA, 8 epilogue warps
+constexpr int kTcMaxMt = 8;       // upper bound of M-tiles per tile (min(8, kAccCols / CP) at run time)
 constexpr int kAccCols = 256;     // TMEM columns per accumulator buffer
 constexpr int kMaxStages = 8;
 constexpr long long kSpinLimitCycles = 4000000000ll;
@@ -77,6 +79,21 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// 1-D bulk copy global -> shared (weights), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -100,6 +117,30 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same, with descriptors given as {lo, shared hi} words and the accumulate flag at compile time.
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                              uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "n"(kAccumulate ? 1 : 0)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_lohi_rt(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
@@ -145,7 +186,8 @@ struct TcConvParams {
   const float* bn_shift;       // [CP]
   const __nv_bfloat16* prev_in;
   __nv_bfloat16* prev_out;
-  __nv_bfloat16* y;
+  __nv_bfloat16* y;            // nullptr: do not store the BN output (last layer with fused pooling)
+  float* pool_sum;             // [B][CP] per-utterance sums of the BN output over H*W, or nullptr
   int B, total_tiles;
   TcGeom g;
 };
@@ -156,12 +198,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
   constexpr int CP = 16 * NKC;       // padded channels = UMMA N
   constexpr int NP = 2 * NKC;        // 8-channel planes
   constexpr int W_HALF = CP * 16;    // bytes of one [CP][8] weight half-slab
+  constexpr int W_BYTES = 9 * NKC * 2 * W_HALF;
   extern __shared__ __align__(1024) unsigned char smem[];
   const TcGeom& g = p.g;
 
   // ---- shared memory carve-up
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);            // full[8], empty[8], tfull[2], tempty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 20);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);   // full[8], empty[8], tfull[2], tempty[2], wfull
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 24);
   float* s_scale = reinterpret_cast<float*>(smem + 256);          // [CP]
   float* s_shift = s_scale + CP;                                  // [CP]
   unsigned char* s_w = smem + g.smem_w_off;
@@ -171,24 +214,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
+  const uint32_t wfull_bar = bar0 + 8u * (2 * kMaxStages + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kTcEpiWarps); }
+    mbar_init(wfull_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap);
+    // weights: one asynchronous bulk copy global -> shared, completion on wfull_bar
+    mbar_expect_tx(wfull_bar, W_BYTES);
+    bulk_load(smem_u32(s_w), p.wpack, W_BYTES, wfull_bar);
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(p.wpack);
-    uint4* dst = reinterpret_cast<uint4*>(s_w);
-    for (int i = threadIdx.x; i < 9 * NKC * 2 * CP; i += kTcThreads) dst[i] = __ldg(src + i);
-    for (int i = threadIdx.x; i < CP; i += kTcThreads) { s_scale[i] = p.bn_scale[i]; s_shift[i] = p.bn_shift[i]; }
-    fence_async_smem();   // generic-proxy writes -> visible to the async proxy (UMMA reads s_w)
-  }
+  for (int i = threadIdx.x; i < CP; i += kTcThreads) { s_scale[i] = p.bn_scale[i]; s_shift[i] = p.bn_shift[i]; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -200,7 +243,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (uint32_t)(2 * g.n_boxes * g.rows_box * g.Wp * 16);
@@ -221,32 +264,52 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
+    // Everything below is warp-uniform.  A descriptor = {lo: addr>>4 | (LBO>>4)<<16, hi: SBO>>4 | version};
+    // per MMA only the 14-bit address field of `lo` changes, by a precomputed 16-byte-unit offset.
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     constexpr uint32_t idesc = umma_idesc(128, CP);
-    const uint32_t w_base = smem_u32(s_w);
+    constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo_fields = ((uint32_t)(g.slab_bytes >> 4) & 0x3FFFu) << 16;
+    const uint32_t b_lo_base = ((smem_u32(s_w) >> 4) & 0x3FFFu) | (((uint32_t)(W_HALF >> 4) & 0x3FFFu) << 16);
+    int tap16[9];   // start offset of tap (dh,dw) inside a stage, in 16-byte units (may be negative)
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 3; ++dw) tap16[dh * 3 + dw] = (g.tap_off[dh] >> 4) + (dw - 1) * g.d;
+    const bool side = g.side_taps != 0;
+    const int first_tap = side ? 0 : 1;
+    constexpr int MAXMT = (kAccCols / CP) < kTcMaxMt ? (kAccCols / CP) : kTcMaxMt;
+    const bool leader = elect_one();
+    mbar_wait(wfull_bar, 0);   // weights have landed
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int tix = t % tiles_per_utt;
       const int n_mt = tile_mt(tix);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
+      const uint32_t d_base = tmem_base + acc * kAccCols;
+#pragma unroll
       for (int kc = 0; kc < NKC; ++kc) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sbase = smem_u32(s_ring + (size_t)stage * g.stage_bytes);
-          bool first = (kc == 0);
-          for (int dh = 0; dh < 3; ++dh) {
-            for (int dw = 0; dw < 3; ++dw) {
-              if (dw != 1 && !g.side_taps) continue;
-              const uint32_t a0 = sbase + g.tap_off[dh] + (dw - 1) * g.d * 16;
-              const uint64_t bdesc =
-                  umma_desc(w_base + (((dh * 3 + dw) * NKC + kc) * 2) * W_HALF, W_HALF, 128);
-              for (int mt = 0; mt < n_mt; ++mt) {
-                const uint64_t adesc = umma_desc(a0 + mt * 2048, g.slab_bytes, 128);
-                umma_f16(tmem_base + acc * kAccCols + mt * CP, adesc, bdesc, idesc, first ? 0u : 1u);
-              }
-              first = false;
+        if (leader) {
+          const uint32_t a_lo_stage =
+              ((smem_u32(s_ring + (size_t)stage * g.stage_bytes) >> 4) & 0x3FFFu) | a_lo_fields;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            if ((tap % 3) != 1 && !side) continue;
+            const uint32_t a_lo = a_lo_stage + (uint32_t)tap16[tap];
+            const uint32_t b_lo = b_lo_base + (uint32_t)(((tap * NKC + kc) * 2 * W_HALF) >> 4);
+            if (kc == 0 && tap <= 1) {
+              // the first tap of a tile overwrites the accumulators (tap 0, or tap 1 when d >= W)
+              const uint32_t accum = (tap == first_tap) ? 0u : 1u;
+#pragma unroll
+              for (int mt = 0; mt < MAXMT; ++mt)
+                if (mt < n_mt) umma_f16_lohi_rt(d_base + mt * CP, a_lo + mt * 128, b_lo, desc_hi, idesc, accum);
+            } else {
+#pragma unroll
+              for (int mt = 0; mt < MAXMT; ++mt)
+                if (mt < n_mt) umma_f16_lohi<true>(d_base + mt * CP, a_lo + mt * 128, b_lo, desc_hi, idesc);
             }
           }
           umma_commit(empty_bar(stage));                       // stage reusable once these MMAs retire
@@ -259,63 +322,86 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ================================ epilogue ================================
-    const int q = warp & 3;   // TMEM lane quarter this warp may read
+    // ================================ epilogue (8 warps) ================================
+    // TMEM lane quarter q = warp % 4 is fixed by hardware; the two warps that share a quarter
+    // take alternate M-tiles.
+    const int q = warp & 3;
+    const int par = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool has_prev = p.prev_in != nullptr;
+    const int64_t plane_stride = (int64_t)g.H * g.W;   // in 16-byte (8-channel) units
+    const uint4* prev_in = reinterpret_cast<const uint4*>(p.prev_in);
+    uint4* prev_out = reinterpret_cast<uint4*>(p.prev_out);
+    uint4* y_out = reinterpret_cast<uint4*>(p.y);
+    const bool do_pool = p.pool_sum != nullptr;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      float psum[CP];   // this thread's share of sum_{h,w} BN(x) for the tile (fused global mean, resnet.py:57-58)
+#pragma unroll
+      for (int c = 0; c < CP; ++c) psum[c] = 0.f;
       const int b = t / tiles_per_utt, tix = t - b * tiles_per_utt;
       const int h0 = tix * g.R;
       const int rows = tile_rows(tix);
       const int n_mt = tile_mt(tix);
+      const int64_t utt_base = ((int64_t)b * NP) * plane_stride + (int64_t)h0 * g.W;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      for (int mt = 0; mt < n_mt; ++mt) {
+      for (int mt = par; mt < n_mt; mt += 2) {
         const int pos = mt * 128 + q * 32 + lane;
         const int r = pos / g.Wp;
         const int w = pos - r * g.Wp - g.dpad;
         const bool valid = (w >= 0) && (r < rows);
-        const int64_t pix = ((int64_t)(h0 + r) * g.W + w);
-        const int64_t plane_stride = (int64_t)g.H * g.W;   // in 8-channel units
-        const int64_t base = ((int64_t)b * NP) * plane_stride + pix;
+        const int64_t base = utt_base + (int64_t)r * g.W + w;
+        uint4 pv[NP];
+        if (has_prev && valid) {
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) pv[pl] = __ldg(prev_in + base + pl * plane_stride);
+        }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP;
+        uint32_t v[NKC][16];
 #pragma unroll
-        for (int j = 0; j < NKC; ++j) {
-          uint32_t v[16];
-          tmem_ld16(taddr + 16 * j, v);
-          tmem_ld_wait();
-          if (valid) {
+        for (int j = 0; j < NKC; ++j) tmem_ld16(taddr + 16 * j, v[j]);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const int64_t off = base + (int64_t)(2 * j + hf) * plane_stride;   // uint4 units
-              float x[8];
+          for (int pl = 0; pl < NP; ++pl) {
+            float x[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[8 * hf + e]), 0.f);
-              if (has_prev) {
-                const uint4 pv = __ldg(reinterpret_cast<const uint4*>(p.prev_in) + off);
-                const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(pb[e]);
-                  x[2 * e] += f.x;
-                  x[2 * e + 1] += f.y;
-                }
-                uint4 po;
-                __nv_bfloat162* pob = reinterpret_cast<__nv_bfloat162*>(&po);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) pob[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-                reinterpret_cast<uint4*>(p.prev_out)[off] = po;
-              }
-              uint4 yo;
-              __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
+            for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[pl >> 1][8 * (pl & 1) + e]), 0.f);
+            if (has_prev) {
+              const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[pl]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int c = 16 * j + 8 * hf + 2 * e;
-                yb[e] = __floats2bfloat162_rn(fmaf(x[2 * e], s_scale[c], s_shift[c]),
-                                              fmaf(x[2 * e + 1], s_scale[c + 1], s_shift[c + 1]));
+                const float2 f = __bfloat1622float2(pb[e]);
+                x[2 * e] += f.x;
+                x[2 * e + 1] += f.y;
               }
-              reinterpret_cast<uint4*>(p.y)[off] = yo;
+              uint4 po;
+              __nv_bfloat162* pob = reinterpret_cast<__nv_bfloat162*>(&po);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) pob[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+              prev_out[base + pl * plane_stride] = po;
+            }
+            uint4 yo;
+            __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
+            const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + 8 * pl);
+            const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + 8 * pl + 4);
+            const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + 8 * pl);
+            const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + 8 * pl + 4);
+            const float y0 = fmaf(x[0], sc0.x, sh0.x), y1 = fmaf(x[1], sc0.y, sh0.y);
+            const float y2 = fmaf(x[2], sc0.z, sh0.z), y3 = fmaf(x[3], sc0.w, sh0.w);
+            const float y4 = fmaf(x[4], sc1.x, sh1.x), y5 = fmaf(x[5], sc1.y, sh1.y);
+            const float y6 = fmaf(x[6], sc1.z, sh1.z), y7 = fmaf(x[7], sc1.w, sh1.w);
+            if (do_pool) {
+              psum[8 * pl + 0] += y0; psum[8 * pl + 1] += y1; psum[8 * pl + 2] += y2; psum[8 * pl + 3] += y3;
+              psum[8 * pl + 4] += y4; psum[8 * pl + 5] += y5; psum[8 * pl + 6] += y6; psum[8 * pl + 7] += y7;
+            }
+            if (y_out != nullptr) {
+              yb[0] = __floats2bfloat162_rn(y0, y1);
+              yb[1] = __floats2bfloat162_rn(y2, y3);
+              yb[2] = __floats2bfloat162_rn(y4, y5);
+              yb[3] = __floats2bfloat162_rn(y6, y7);
+              y_out[base + pl * plane_stride] = yo;
             }
           }
         }
@@ -325,6 +411,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if (do_pool) {
+        // the tile belongs to one utterance: warp-reduce the 32 positions, one atomic per channel
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+          float v = psum[c];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == (c & 31)) atomicAdd(p.pool_sum + (int64_t)b * CP + c, v);
+        }
+      }
     }
   }
 
@@ -342,7 +438,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
 // One thread per output pixel; channels in groups of 8 -> one 16-byte store per plane.
 __global__ void __launch_bounds__(256)
 conv0_p8_kernel(const float* __restrict__ feat, const float* __restrict__ w0, __nv_bfloat16* __restrict__ out,
-                int T, int F, int C, int NP, int ph, int pw, int Ho, int Wo, int rows_per_tile) {
+                float* __restrict__ pool_sum, int T, int F, int C, int NP, int ph, int pw, int Ho, int Wo,
+                int rows_per_tile) {
+  if (pool_sum != nullptr && blockIdx.x == 0 && threadIdx.x < NP * 8)
+    pool_sum[(int64_t)blockIdx.y * NP * 8 + threadIdx.x] = 0.f;
   extern __shared__ __align__(16) float smem_f[];
   const int in_rows = rows_per_tile * ph + 2, in_cols = F + 2;
   float* s_in = smem_f;
@@ -396,6 +495,86 @@ conv0_p8_kernel(const float* __restrict__ feat, const float* __restrict__ w0, __
     for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(acc[2 * e] * inv, acc[2 * e + 1] * inv);
     dst[pl * plane_stride] = o;
   }
+}
+
+// conv_0 without pooling (res15): each thread computes 4 consecutive pixels x all channels, so
+// every weight read from shared memory feeds 4 FMAs; stores are 64 contiguous bytes per plane.
+constexpr int kC0Px = 4;
+__global__ void __launch_bounds__(256)
+conv0_p8_w4_kernel(const float* __restrict__ feat, const float* __restrict__ w0, __nv_bfloat16* __restrict__ out,
+                   float* __restrict__ pool_sum, int T, int F, int C, int NP, int groups_per_row,
+                   int rows_per_tile) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int in_rows = rows_per_tile + 2, in_cols = groups_per_row * kC0Px + 2;
+  float* s_in = smem_f;
+  float* s_w = smem_f + round_up(in_rows * in_cols, 4);   // [NP*8][12]
+  const int64_t b = blockIdx.y;
+  const int h0 = blockIdx.x * rows_per_tile;
+  if (pool_sum != nullptr && blockIdx.x == 0 && threadIdx.x < NP * 8) pool_sum[b * NP * 8 + threadIdx.x] = 0.f;
+  const float* src = feat + b * (int64_t)T * F;
+  for (int i = threadIdx.x; i < in_rows * in_cols; i += blockDim.x) {
+    const int r = i / in_cols, c = i - r * in_cols;
+    const int h = h0 - 1 + r, w = c - 1;
+    s_in[i] = (h >= 0 && h < T && w >= 0 && w < F) ? __ldg(src + (int64_t)h * F + w) : 0.f;
+  }
+  for (int i = threadIdx.x; i < NP * 8 * 12; i += blockDim.x) {
+    const int c = i / 12, k = i - c * 12;
+    s_w[i] = (k < 9 && c < C) ? __ldg(w0 + c * 9 + k) : 0.f;
+  }
+  __syncthreads();
+  const int r = threadIdx.x / groups_per_row, gx = threadIdx.x - r * groups_per_row;
+  const int h = h0 + r;
+  if (r >= rows_per_tile || h >= T) return;
+  const int w0px = gx * kC0Px;
+  float pch[3][kC0Px + 2];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int e = 0; e < kC0Px + 2; ++e) pch[a][e] = s_in[(r + a) * in_cols + w0px + e];
+  const int64_t plane_stride = (int64_t)T * F;
+  uint4* dst = reinterpret_cast<uint4*>(out) + (b * NP) * plane_stride + (int64_t)h * F + w0px;
+  for (int pl = 0; pl < NP; ++pl) {
+    float acc[kC0Px][8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float* wc = s_w + (pl * 8 + e) * 12;
+      const float4 wa = *reinterpret_cast<const float4*>(wc);
+      const float4 wb = *reinterpret_cast<const float4*>(wc + 4);
+      const float w8 = wc[8];
+#pragma unroll
+      for (int px = 0; px < kC0Px; ++px) {
+        float v = pch[0][px] * wa.x;
+        v = fmaf(pch[0][px + 1], wa.y, v); v = fmaf(pch[0][px + 2], wa.z, v);
+        v = fmaf(pch[1][px], wa.w, v); v = fmaf(pch[1][px + 1], wb.x, v); v = fmaf(pch[1][px + 2], wb.y, v);
+        v = fmaf(pch[2][px], wb.z, v); v = fmaf(pch[2][px + 1], wb.w, v); v = fmaf(pch[2][px + 2], w8, v);
+        acc[px][e] = fmaxf(v, 0.f);
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < kC0Px; ++px) {
+      if (w0px + px < F) {
+        uint4 o;
+        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(acc[px][2 * e], acc[px][2 * e + 1]);
+        dst[pl * plane_stride + px] = o;
+      }
+    }
+  }
+}
+
+// Linear on the pooled sums produced by the last convolution's epilogue (resnet.py:57-59).
+__global__ void __launch_bounds__(256)
+tail_pool_kernel(const float* __restrict__ pool_sum, const float* __restrict__ out_w, const float* __restrict__ out_b,
+                 float* __restrict__ logits, int64_t B, int C, int CP, int HW, int n_labels) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n_labels) return;
+  const int64_t b = i / n_labels;
+  const int l = (int)(i - b * n_labels);
+  const float inv = 1.f / (float)HW;
+  float v = __ldg(out_b + l);
+  for (int c = 0; c < C; ++c) v = fmaf(pool_sum[b * CP + c] * inv, __ldg(out_w + l * C + c), v);
+  logits[i] = v;
 }
 
 // mean over H*W of planar-8 bf16 + Linear (resnet.py:57-59).  One CTA per utterance.
@@ -501,7 +680,7 @@ struct TcResNet {
   std::map<std::tuple<const void*, int64_t, int, int, int>, CUtensorMap> maps;
 };
 
-static int tc_max_mt(int CP) { return std::min(8, kAccCols / CP); }
+static int tc_max_mt(int CP) { return std::min(kTcMaxMt, kAccCols / CP); }
 
 // Tile geometry of one layer launch.  Returns false if the layer cannot be tiled.
 static bool tc_geom(int NKC, int H, int W, int d, TcGeom* g) {
@@ -646,7 +825,7 @@ size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int
   tc_map_hw(p->cfg, T, F, &H, &W);
   if (H < 1 || W < 1 || W > 256 || !tc_layers_ok(p, H, W)) return 0;
   const int64_t c = tc_chunk(p, B, H, W, chunk);
-  return 3 * round_up<size_t>((size_t)c * p->NP * H * W * 16, 1024);
+  return 3 * round_up<size_t>((size_t)c * p->NP * H * W * 16, 1024) + round_up<size_t>((size_t)c * p->CP * 4, 1024);
 }
 
 static int tc_get_map(TcResNet* p, const void* base, int64_t planes, int H, int W, const TcGeom& g, CUtensorMap** out) {
@@ -707,8 +886,14 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
   __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws));
   __nv_bfloat16* A[2] = {reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + buf),
                          reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + 2 * buf)};
+  float* pool = reinterpret_cast<float*>(static_cast<char*>(ws) + 3 * buf);
+  const bool fuse_pool = c.n_layers >= 1;
   const int ph = c.pool_h > 0 ? c.pool_h : 1, pw = c.pool_w > 0 ? c.pool_w : 1;
   KWS_REQUIRE(W <= 256, "conv_0: map width %d exceeds 256", W);
+  const bool fast0 = (ph == 1 && pw == 1);
+  const int groups0 = ceil_div(W, kC0Px);
+  const int rows0f = std::max(1, std::min(H, 256 / groups0));
+  const size_t smem0f = sizeof(float) * (round_up((rows0f + 2) * (groups0 * kC0Px + 2), 4) + p->NP * 8 * 12);
   const int rows0 = std::max(1, std::min(H, 256 / W));
   const size_t smem0 = sizeof(float) * (round_up((rows0 * ph + 2) * (F + 2), 4) + p->NP * 8 * 12);
   KWS_REQUIRE(smem0 <= 48 * 1024, "conv_0: tile needs %zu bytes of shared memory", smem0);
@@ -716,8 +901,14 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     const int64_t nb = std::min(chunk, B - b0);
     if (prof) prof->tick(1, st);
-    conv0_p8_kernel<<<dim3(ceil_div(H, rows0), (unsigned)nb), 256, smem0, st>>>(
-        feat + b0 * (int64_t)T * F, p->conv0_w, P, T, F, c.n_maps, p->NP, ph, pw, H, W, rows0);
+    if (fast0 && smem0f <= 48 * 1024)
+      conv0_p8_w4_kernel<<<dim3(ceil_div(H, rows0f), (unsigned)nb), 256, smem0f, st>>>(
+          feat + b0 * (int64_t)T * F, p->conv0_w, P, fuse_pool ? pool : nullptr, T, F, c.n_maps, p->NP, groups0,
+          rows0f);
+    else
+      conv0_p8_kernel<<<dim3(ceil_div(H, rows0), (unsigned)nb), 256, smem0, st>>>(
+          feat + b0 * (int64_t)T * F, p->conv0_w, P, fuse_pool ? pool : nullptr, T, F, c.n_maps, p->NP, ph, pw, H,
+          W, rows0);
     KWS_CHECK_LAUNCH();
     const __nv_bfloat16* x = P;
     int flip = 0;
@@ -732,7 +923,9 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
       prm.bn_shift = p->shift_p[i - 1];
       prm.prev_in = (i % 2 == 0) ? P : nullptr;
       prm.prev_out = (i % 2 == 0) ? P : nullptr;
-      prm.y = A[flip];
+      const bool last = (i == c.n_layers);
+      prm.y = last ? nullptr : A[flip];
+      prm.pool_sum = last ? pool : nullptr;
       prm.B = (int)nb;
       prm.total_tiles = (int)nb * prm.g.tiles_per_utt;
       const int grid = std::min(p->n_sms, prm.total_tiles);
@@ -747,8 +940,12 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
       flip ^= 1;
     }
     if (prof) prof->tick(1, st);
-    tail_p8_kernel<<<(unsigned)nb, 256, 0, st>>>(x, p->out_w, p->out_b, logits + b0 * c.n_labels, c.n_maps, p->NP,
-                                                 H * W, c.n_labels);
+    if (fuse_pool)
+      tail_pool_kernel<<<(unsigned)ceil_div<int64_t>(nb * c.n_labels, 256), 256, 0, st>>>(
+          pool, p->out_w, p->out_b, logits + b0 * c.n_labels, nb, c.n_maps, p->CP, H * W, c.n_labels);
+    else
+      tail_p8_kernel<<<(unsigned)nb, 256, 0, st>>>(x, p->out_w, p->out_b, logits + b0 * c.n_labels, c.n_maps, p->NP,
+                                                   H * W, c.n_labels);
     KWS_CHECK_LAUNCH();
   }
   return KWS_OK;
