@@ -32,7 +32,8 @@
 namespace kws {
 
 constexpr int kTcEpiWarps = 8;
-constexpr int kTcThreads = 32 * (2 + kTcEpiWarps);   // warp 0 TMA, warp 1 MMA, 8 epilogue warps
+constexpr int kTcIssuers = 4;      // MMA-issuing warps (M-tiles dealt round-robin)
+constexpr int kTcThreads = 32 * (1 + kTcIssuers + kTcEpiWarps);   // warp 0 TMA, warps 1-4 MMA, 8 epilogue warps
 constexpr int kTcMaxMt = 8;       // upper bound of M-tiles per tile (min(8, kAccCols / CP) at run time)
 constexpr int kAccCols = 256;     // TMEM columns per accumulator buffer
 constexpr int kMaxStages = 8;
@@ -181,32 +182,34 @@ struct TcGeom {
 };
 
 struct TcConvParams {
-  const __nv_bfloat16* wpack;  // [9][NKC][2][CP][8]
-  const float* bn_scale;       // [CP] (0 for pad channels)
-  const float* bn_shift;       // [CP]
+  const __nv_bfloat16* wpack;  // [9][NKC][2][CP][8]; input-channel axis pre-multiplied by the previous layer's BN scale
+  const float* neg_mean;       // [CP] -running_mean of this layer's BatchNorm (0 for pad channels)
   const __nv_bfloat16* prev_in;
   __nv_bfloat16* prev_out;
-  __nv_bfloat16* y;            // nullptr: do not store the BN output (last layer with fused pooling)
-  float* pool_sum;             // [B][CP] per-utterance sums of the BN output over H*W, or nullptr
+  __nv_bfloat16* y;            // centred activation z = x - mean (the 1/sigma factor lives in the next layer's weights)
+  float* pool_sum;             // [B][CP] per-utterance sums of z over H*W (last layer), or nullptr
   int B, total_tiles;
   TcGeom g;
 };
 
-template <int NKC>
+// HAS_PREV: even layer (adds and rewrites the skip tensor).  DO_POOL: last layer (accumulates the
+// global mean instead of storing the activation).
+template <int NKC, bool HAS_PREV, bool DO_POOL>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p) {
   constexpr int CP = 16 * NKC;       // padded channels = UMMA N
   constexpr int NP = 2 * NKC;        // 8-channel planes
   constexpr int W_HALF = CP * 16;    // bytes of one [CP][8] weight half-slab
   constexpr int W_BYTES = 9 * NKC * 2 * W_HALF;
+  constexpr int MAXMT = (kAccCols / CP) < kTcMaxMt ? (kAccCols / CP) : kTcMaxMt;
+  constexpr int MAXU = (MAXMT + kTcIssuers - 1) / kTcIssuers;   // M-tiles per issuer warp
   extern __shared__ __align__(1024) unsigned char smem[];
   const TcGeom& g = p.g;
 
   // ---- shared memory carve-up
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);   // full[8], empty[8], tfull[2], tempty[2], wfull
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 24);
-  float* s_scale = reinterpret_cast<float*>(smem + 256);          // [CP]
-  float* s_shift = s_scale + CP;                                  // [CP]
+  float* s_negmean = reinterpret_cast<float*>(smem + 256);        // [CP]
   unsigned char* s_w = smem + g.smem_w_off;
   unsigned char* s_ring = smem + g.smem_ring_off;
   const uint32_t bar0 = smem_u32(bars);
@@ -221,8 +224,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
-    for (int s = 0; s < g.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kTcEpiWarps); }
+    for (int s = 0; s < g.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kTcIssuers); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), kTcIssuers); mbar_init(tempty_bar(a), kTcEpiWarps); }
     mbar_init(wfull_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap);
@@ -231,7 +234,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
     bulk_load(smem_u32(s_w), p.wpack, W_BYTES, wfull_bar);
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  for (int i = threadIdx.x; i < CP; i += kTcThreads) { s_scale[i] = p.bn_scale[i]; s_shift[i] = p.bn_shift[i]; }
+  for (int i = threadIdx.x; i < CP; i += kTcThreads) s_negmean[i] = p.neg_mean[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -262,10 +265,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    // Everything below is warp-uniform.  A descriptor = {lo: addr>>4 | (LBO>>4)<<16, hi: SBO>>4 | version};
+  } else if (warp <= kTcIssuers) {
+    // ================================ MMA issuers (4 warps) ================================
+    // A 128 x CP x 16 MMA lasts ~CP/2 tensor-pipe cycles, less than one thread needs to set up and
+    // issue it, so the M-tiles of a tile are dealt round-robin to kTcIssuers warps (disjoint TMEM
+    // accumulators, hence no ordering between them); every issuer commits to the same barriers.
+    // All operands are warp-uniform.  A descriptor = {lo: addr>>4 | (LBO>>4)<<16, hi: SBO>>4 | version};
     // per MMA only the 14-bit address field of `lo` changes, by a precomputed 16-byte-unit offset.
+    const int me = warp - 1;
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     constexpr uint32_t idesc = umma_idesc(128, CP);
@@ -279,7 +286,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       for (int dw = 0; dw < 3; ++dw) tap16[dh * 3 + dw] = (g.tap_off[dh] >> 4) + (dw - 1) * g.d;
     const bool side = g.side_taps != 0;
     const int first_tap = side ? 0 : 1;
-    constexpr int MAXMT = (kAccCols / CP) < kTcMaxMt ? (kAccCols / CP) : kTcMaxMt;
     const bool leader = elect_one();
     mbar_wait(wfull_bar, 0);   // weights have landed
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -287,14 +293,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       const int n_mt = tile_mt(tix);
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_base = tmem_base + acc * kAccCols;
+      const uint32_t d_base = tmem_base + acc * kAccCols + me * CP;
 #pragma unroll
       for (int kc = 0; kc < NKC; ++kc) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (leader) {
           const uint32_t a_lo_stage =
-              ((smem_u32(s_ring + (size_t)stage * g.stage_bytes) >> 4) & 0x3FFFu) | a_lo_fields;
+              (((smem_u32(s_ring + (size_t)stage * g.stage_bytes) >> 4) + me * 128) & 0x3FFFu) | a_lo_fields;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             if ((tap % 3) != 1 && !side) continue;
@@ -304,12 +310,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
               // the first tap of a tile overwrites the accumulators (tap 0, or tap 1 when d >= W)
               const uint32_t accum = (tap == first_tap) ? 0u : 1u;
 #pragma unroll
-              for (int mt = 0; mt < MAXMT; ++mt)
-                if (mt < n_mt) umma_f16_lohi_rt(d_base + mt * CP, a_lo + mt * 128, b_lo, desc_hi, idesc, accum);
+              for (int u = 0; u < MAXU; ++u)
+                if (me + u * kTcIssuers < n_mt)
+                  umma_f16_lohi_rt(d_base + u * kTcIssuers * CP, a_lo + u * kTcIssuers * 128, b_lo, desc_hi, idesc, accum);
             } else {
 #pragma unroll
-              for (int mt = 0; mt < MAXMT; ++mt)
-                if (mt < n_mt) umma_f16_lohi<true>(d_base + mt * CP, a_lo + mt * 128, b_lo, desc_hi, idesc);
+              for (int u = 0; u < MAXU; ++u)
+                if (me + u * kTcIssuers < n_mt)
+                  umma_f16_lohi<true>(d_base + u * kTcIssuers * CP, a_lo + u * kTcIssuers * 128, b_lo, desc_hi, idesc);
             }
           }
           umma_commit(empty_bar(stage));                       // stage reusable once these MMAs retire
@@ -324,21 +332,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
   } else {
     // ================================ epilogue (8 warps) ================================
     // TMEM lane quarter q = warp % 4 is fixed by hardware; the two warps that share a quarter
-    // take alternate M-tiles.
+    // take alternate M-tiles.  z = ReLU(acc) (+ skip) - mean, per channel; the per-channel
+    // constants live in registers (pooling variant: shared memory, it needs the registers for sums).
+    const int ew = warp - (1 + kTcIssuers);
     const int q = warp & 3;
-    const int par = (warp - 2) >> 2;
+    const int par = ew >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool has_prev = p.prev_in != nullptr;
     const int64_t plane_stride = (int64_t)g.H * g.W;   // in 16-byte (8-channel) units
     const uint4* prev_in = reinterpret_cast<const uint4*>(p.prev_in);
     uint4* prev_out = reinterpret_cast<uint4*>(p.prev_out);
     uint4* y_out = reinterpret_cast<uint4*>(p.y);
-    const bool do_pool = p.pool_sum != nullptr;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      float psum[CP];   // this thread's share of sum_{h,w} BN(x) for the tile (fused global mean, resnet.py:57-58)
+    float nm[DO_POOL ? 1 : CP];
+    if constexpr (!DO_POOL) {
 #pragma unroll
-      for (int c = 0; c < CP; ++c) psum[c] = 0.f;
+      for (int c = 0; c < CP; ++c) nm[c] = s_negmean[c];
+    }
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      float psum[DO_POOL ? CP : 1];   // this thread's share of sum_{h,w} z for the tile (resnet.py:57-58)
+      if constexpr (DO_POOL) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) psum[c] = 0.f;
+      }
       const int b = t / tiles_per_utt, tix = t - b * tiles_per_utt;
       const int h0 = tix * g.R;
       const int rows = tile_rows(tix);
@@ -352,10 +367,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
         const int w = pos - r * g.Wp - g.dpad;
         const bool valid = (w >= 0) && (r < rows);
         const int64_t base = utt_base + (int64_t)r * g.W + w;
-        uint4 pv[NP];
-        if (has_prev && valid) {
+        uint4 pv[HAS_PREV ? NP : 1];
+        if constexpr (HAS_PREV) {
+          if (valid) {
 #pragma unroll
-          for (int pl = 0; pl < NP; ++pl) pv[pl] = __ldg(prev_in + base + pl * plane_stride);
+            for (int pl = 0; pl < NP; ++pl) pv[pl] = __ldg(prev_in + base + pl * plane_stride);
+          }
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP;
         uint32_t v[NKC][16];
@@ -368,7 +385,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
             float x[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[pl >> 1][8 * (pl & 1) + e]), 0.f);
-            if (has_prev) {
+            if constexpr (HAS_PREV) {
               const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[pl]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -382,25 +399,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
               for (int e = 0; e < 4; ++e) pob[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
               prev_out[base + pl * plane_stride] = po;
             }
-            uint4 yo;
-            __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
-            const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + 8 * pl);
-            const float4 sc1 = *reinterpret_cast<const float4*>(s_scale + 8 * pl + 4);
-            const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + 8 * pl);
-            const float4 sh1 = *reinterpret_cast<const float4*>(s_shift + 8 * pl + 4);
-            const float y0 = fmaf(x[0], sc0.x, sh0.x), y1 = fmaf(x[1], sc0.y, sh0.y);
-            const float y2 = fmaf(x[2], sc0.z, sh0.z), y3 = fmaf(x[3], sc0.w, sh0.w);
-            const float y4 = fmaf(x[4], sc1.x, sh1.x), y5 = fmaf(x[5], sc1.y, sh1.y);
-            const float y6 = fmaf(x[6], sc1.z, sh1.z), y7 = fmaf(x[7], sc1.w, sh1.w);
-            if (do_pool) {
-              psum[8 * pl + 0] += y0; psum[8 * pl + 1] += y1; psum[8 * pl + 2] += y2; psum[8 * pl + 3] += y3;
-              psum[8 * pl + 4] += y4; psum[8 * pl + 5] += y5; psum[8 * pl + 6] += y6; psum[8 * pl + 7] += y7;
-            }
-            if (y_out != nullptr) {
-              yb[0] = __floats2bfloat162_rn(y0, y1);
-              yb[1] = __floats2bfloat162_rn(y2, y3);
-              yb[2] = __floats2bfloat162_rn(y4, y5);
-              yb[3] = __floats2bfloat162_rn(y6, y7);
+            if constexpr (DO_POOL) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) psum[8 * pl + e] += x[e] + s_negmean[8 * pl + e];
+            } else {
+              uint4 yo;
+              __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                yb[e] = __floats2bfloat162_rn(x[2 * e] + nm[8 * pl + 2 * e], x[2 * e + 1] + nm[8 * pl + 2 * e + 1]);
               y_out[base + pl * plane_stride] = yo;
             }
           }
@@ -411,14 +418,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-      if (do_pool) {
+      if constexpr (DO_POOL) {
         // the tile belongs to one utterance: warp-reduce the 32 positions, one atomic per channel
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
-          float v = psum[c];
+          float sum = psum[c];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == (c & 31)) atomicAdd(p.pool_sum + (int64_t)b * CP + c, v);
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == (c & 31)) atomicAdd(p.pool_sum + (int64_t)b * CP + c, sum);
         }
       }
     }
@@ -565,15 +572,17 @@ conv0_p8_w4_kernel(const float* __restrict__ feat, const float* __restrict__ w0,
 
 // Linear on the pooled sums produced by the last convolution's epilogue (resnet.py:57-59).
 __global__ void __launch_bounds__(256)
-tail_pool_kernel(const float* __restrict__ pool_sum, const float* __restrict__ out_w, const float* __restrict__ out_b,
-                 float* __restrict__ logits, int64_t B, int C, int CP, int HW, int n_labels) {
+tail_pool_kernel(const float* __restrict__ pool_sum, const float* __restrict__ scale, const float* __restrict__ out_w,
+                 const float* __restrict__ out_b, float* __restrict__ logits, int64_t B, int C, int CP, int HW,
+                 int n_labels) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * n_labels) return;
   const int64_t b = i / n_labels;
   const int l = (int)(i - b * n_labels);
   const float inv = 1.f / (float)HW;
   float v = __ldg(out_b + l);
-  for (int c = 0; c < C; ++c) v = fmaf(pool_sum[b * CP + c] * inv, __ldg(out_w + l * C + c), v);
+  // pool_sum holds sums of z = x - mean; BatchNorm output mean = z_mean / sigma (resnet.py:55-58)
+  for (int c = 0; c < C; ++c) v = fmaf(pool_sum[b * CP + c] * inv * __ldg(scale + c), __ldg(out_w + l * C + c), v);
   logits[i] = v;
 }
 
@@ -622,7 +631,10 @@ tail_p8_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ ou
 }
 
 // torch [C][C][3][3] fp32 -> [9][NKC][2][CP][8] bf16 (tap, 16-ch chunk, K half, cout, 8 cin)
-__global__ void pack_conv3x3_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int C, int NKC) {
+// `in_scale` (nullable): BN scale 1/sigma of the PREVIOUS layer, folded into the input-channel axis
+// (exact: the convolution is linear and zero padding stays zero).
+__global__ void pack_conv3x3_tc_kernel(const float* __restrict__ w, const float* __restrict__ in_scale,
+                                       __nv_bfloat16* __restrict__ out, int C, int NKC) {
   const int CP = 16 * NKC;
   const int total = 9 * NKC * 2 * CP * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -633,17 +645,18 @@ __global__ void pack_conv3x3_tc_kernel(const float* __restrict__ w, __nv_bfloat1
     const int kc = t % NKC;
     const int tap = t / NKC;
     const int ci = kc * 16 + half * 8 + e;
-    const float v = (co < C && ci < C) ? w[((int64_t)co * C + ci) * 9 + tap] : 0.f;
+    float v = (co < C && ci < C) ? w[((int64_t)co * C + ci) * 9 + tap] : 0.f;
+    if (in_scale != nullptr && ci < C) v *= in_scale[ci];
     out[i] = __float2bfloat16_rn(v);
   }
 }
 
-__global__ void pad_bn_kernel(const float* __restrict__ scale, const float* __restrict__ shift,
+__global__ void pad_bn_kernel(const float* __restrict__ scale, const float* __restrict__ mean,
                               float* __restrict__ scale_p, float* __restrict__ shift_p, int C, int CP) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < CP) {
     scale_p[c] = c < C ? scale[c] : 0.f;
-    shift_p[c] = c < C ? shift[c] : 0.f;
+    shift_p[c] = c < C ? -mean[c] : 0.f;   // the epilogue adds -mean; 1/sigma is folded into the next layer
   }
 }
 
@@ -673,7 +686,7 @@ struct TcResNet {
   int n_sms = 148;
   void* blob = nullptr;
   std::vector<__nv_bfloat16*> wpack;        // per layer
-  std::vector<float*> scale_p, shift_p;     // per layer, padded to CP
+  std::vector<float*> scale_p, shift_p;     // per layer, padded to CP: BN 1/sigma and -running_mean
   float* conv0_w = nullptr;                 // [C][9]
   float* out_w = nullptr;
   float* out_b = nullptr;
@@ -780,9 +793,10 @@ int tc_resnet_set_weights(TcResNet* p, const kws_resnet_weights& w, float* const
   if (!p->supported) return KWS_OK;
   const int C = p->cfg.n_maps, n = p->cfg.n_layers, L = p->cfg.n_labels;
   for (int i = 0; i < n; ++i) {
-    pack_conv3x3_tc_kernel<<<ceil_div(9 * p->NKC * 2 * p->CP * 8, 256), 256, 0, st>>>(w.conv_w[i], p->wpack[i], C, p->NKC);
+    pack_conv3x3_tc_kernel<<<ceil_div(9 * p->NKC * 2 * p->CP * 8, 256), 256, 0, st>>>(
+        w.conv_w[i], i > 0 ? bn_scale[i - 1] : nullptr, p->wpack[i], C, p->NKC);
     KWS_CUDA(cudaGetLastError());
-    pad_bn_kernel<<<1, 64, 0, st>>>(bn_scale[i], bn_shift[i], p->scale_p[i], p->shift_p[i], C, p->CP);
+    pad_bn_kernel<<<1, 64, 0, st>>>(bn_scale[i], w.bn_mean[i], p->scale_p[i], p->shift_p[i], C, p->CP);
     KWS_CUDA(cudaGetLastError());
   }
   KWS_CUDA(cudaMemcpyAsync(p->conv0_w, w.conv0_w, sizeof(float) * C * 9, cudaMemcpyDeviceToDevice, st));
@@ -852,13 +866,22 @@ static int tc_get_map(TcResNet* p, const void* base, int64_t planes, int H, int 
   return KWS_OK;
 }
 
-template <int NKC>
-static int tc_launch_conv(const CUtensorMap& map, const TcConvParams& prm, int grid, cudaStream_t st) {
-  KWS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NKC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int NKC, bool HAS_PREV, bool DO_POOL>
+static int tc_launch_conv3(const CUtensorMap& map, const TcConvParams& prm, int grid, cudaStream_t st) {
+  KWS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NKC, HAS_PREV, DO_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 prm.g.smem_total));
-  conv3x3_tc_kernel<NKC><<<grid, kTcThreads, prm.g.smem_total, st>>>(map, prm);
+  conv3x3_tc_kernel<NKC, HAS_PREV, DO_POOL><<<grid, kTcThreads, prm.g.smem_total, st>>>(map, prm);
   KWS_CHECK_LAUNCH();
   return KWS_OK;
+}
+
+template <int NKC>
+static int tc_launch_conv(const CUtensorMap& map, const TcConvParams& prm, int grid, cudaStream_t st) {
+  const bool prev = prm.prev_in != nullptr, pool = prm.pool_sum != nullptr;
+  if (prev && pool) return tc_launch_conv3<NKC, true, true>(map, prm, grid, st);
+  if (prev) return tc_launch_conv3<NKC, true, false>(map, prm, grid, st);
+  if (pool) return tc_launch_conv3<NKC, false, true>(map, prm, grid, st);
+  return tc_launch_conv3<NKC, false, false>(map, prm, grid, st);
 }
 
 int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, float* logits, void* ws,
@@ -919,8 +942,7 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
       CUtensorMap* map = nullptr;
       KWS_TRY(tc_get_map(p, x, nb * p->NP, H, W, prm.g, &map));
       prm.wpack = p->wpack[i - 1];
-      prm.bn_scale = p->scale_p[i - 1];
-      prm.bn_shift = p->shift_p[i - 1];
+      prm.neg_mean = p->shift_p[i - 1];
       prm.prev_in = (i % 2 == 0) ? P : nullptr;
       prm.prev_out = (i % 2 == 0) ? P : nullptr;
       const bool last = (i == c.n_layers);
@@ -942,7 +964,8 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
     if (prof) prof->tick(1, st);
     if (fuse_pool)
       tail_pool_kernel<<<(unsigned)ceil_div<int64_t>(nb * c.n_labels, 256), 256, 0, st>>>(
-          pool, p->out_w, p->out_b, logits + b0 * c.n_labels, nb, c.n_maps, p->CP, H * W, c.n_labels);
+          pool, p->scale_p[c.n_layers - 1], p->out_w, p->out_b, logits + b0 * c.n_labels, nb, c.n_maps, p->CP, H * W,
+          c.n_labels);
     else
       tail_p8_kernel<<<(unsigned)nb, 256, 0, st>>>(x, p->out_w, p->out_b, logits + b0 * c.n_labels, c.n_maps, p->NP,
                                                    H * W, c.n_labels);

@@ -64,3 +64,19 @@ def harden_(state_dict, seed=1234, scale=1.5):
         elif "conv_" in k and k.endswith("weight"):
             v.mul_(scale)
     return state_dict
+
+
+def calibrate_output_(state_dict, pooled, seed=4321, spread=4.0):
+    """Make argmax parity meaningful (with random weights every
+    utterance maps to one class because the pooled features barely move between utterances).
+    Given pooled features [n, C] of a calibration batch (from the oracle), replace the output
+    layer by W = spread * N(0,1) / std_c and b = -W @ mean, so the logits are driven by the
+    per-utterance DEVIATION of the pooled features and spread over all classes."""
+    g = torch.Generator().manual_seed(seed)
+    w = state_dict["layers.output.weight"]
+    mean = pooled.mean(0)
+    std = pooled.std(0).clamp_min(1e-6)
+    new_w = spread * torch.randn(w.shape, generator=g) / std / (w.shape[1] ** 0.5)
+    w.copy_(new_w)
+    state_dict["layers.output.bias"].copy_(-(new_w @ mean))
+    return state_dict

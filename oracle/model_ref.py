@@ -23,8 +23,9 @@ def resnet_dilation(i, use_dilation):
     return int(2 ** ((i - 1) // 3)) if use_dilation else 1
 
 
-def resnet_forward(sd, config, x):
-    """x: [B, T, F] float32 -> logits [B, n_labels] (resnet.py:38-60)."""
+def resnet_forward(sd, config, x, return_pooled=False):
+    """x: [B, T, F] float32 -> logits [B, n_labels] (resnet.py:38-60).  `return_pooled` also
+    returns the [B, C] input of the output layer (used to calibrate diverse-argmax test weights)."""
     n_layers = config["n_layers"]
     x = x.unsqueeze(1)                                                  # :39
     x = F.relu(F.conv2d(x, sd["layers.conv_0.weight"], padding=1))      # :40-41
@@ -40,7 +41,8 @@ def resnet_forward(sd, config, x):
         x = F.batch_norm(x, sd[f"layers.bn_{i}.running_mean"], sd[f"layers.bn_{i}.running_var"],
                          None, None, False, 0.0, BN_EPS)                # :55 (eval, affine=False)
     x = x.view(x.size(0), x.size(1), -1).mean(2)                        # :57-58
-    return F.linear(x, sd["layers.output.weight"], sd["layers.output.bias"])  # :59
+    y = F.linear(x, sd["layers.output.weight"], sd["layers.output.bias"])  # :59
+    return (y, x) if return_pooled else y
 
 
 def cnn_forward(sd, config, x):

@@ -216,3 +216,79 @@ def test_fp32_full_batch_properties(dev, name):
     got = y[torch.from_numpy(idx).to(dev)].cpu().numpy()
     assert logit_err(got, ref) <= LOGIT_TOL
     assert np.array_equal(got.argmax(1), ref.argmax(1))
+
+
+# ---------------------------------------------------------------------------------------------
+# bf16 tensor-core mode (reported separately, with its own tolerance)
+
+BF16_TOL = 3e-2      # |a-b| <= 3e-2 * max(|b|_inf per row, 1e-3)
+
+
+@pytest.mark.parametrize("name", RESNETS)
+@pytest.mark.parametrize("variant", ["default", "hardened"])
+def test_bf16_logits_vs_reference_golden(dev, name, variant, model_golden):
+    m, _ = gpu_model(name, variant, dev, precision="bf16")
+    x = torch.from_numpy(model_golden["feats"]).to(dev)
+    with torch.no_grad():
+        y = m(x).cpu().numpy()
+    ref = model_golden[f"{name}/{variant}/logits"]
+    assert np.isfinite(y).all()
+    assert logit_err(y, ref) <= BF16_TOL, (name, variant, logit_err(y, ref))
+    assert np.array_equal(y.argmax(1), ref.argmax(1))
+
+
+def _calibrated(name, dev, n_cal=48, seed=21):
+    """Model whose argmax is spread over the classes (output layer calibrated on the oracle)."""
+    kind, cfg = model_config(name)
+    m = honk2_b200.build_model(name)
+    sd = m.state_dict()
+    synth.harden_(sd)
+    cal = torch.from_numpy(mfcc_ref.compute_mfccs_batch(synth.speechlike(n_cal, seed=seed)))
+    _, pooled = model_ref.resnet_forward({k: v.float() for k, v in sd.items() if v.is_floating_point()}, cfg, cal,
+                                         return_pooled=True)
+    synth.calibrate_output_(sd, pooled)
+    return kind, cfg, m, {k: v.clone() for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("name,precision,tol", [("res15", "fp32", LOGIT_TOL), ("res15", "bf16", 6e-2),
+                                                ("res8", "fp32", LOGIT_TOL), ("res8", "bf16", 6e-2)])
+def test_argmax_agreement_with_diverse_classes(dev, name, precision, tol):
+    """100 % argmax agreement on utterances whose oracle top-2 margin exceeds the error bound,
+    with an output layer calibrated so that at least 6 of the 12 classes are hit."""
+    kind, cfg, m, sd = _calibrated(name, dev)
+    m.precision = precision
+    m = m.to(dev)
+    w = synth.speechlike(96, seed=77)
+    ref = model_ref.forward(kind, sd, cfg, torch.from_numpy(mfcc_ref.compute_mfccs_batch(w))).numpy()
+    ap = AudioProcessor()
+    with torch.no_grad():
+        y = m.forward_wave(torch.from_numpy(w).to(dev), ap).cpu().numpy()
+    assert len(set(ref.argmax(1).tolist())) >= 6, "calibration failed to spread the classes"
+    err = np.abs(y - ref).max(axis=1)
+    bound = tol * np.maximum(np.abs(ref).max(axis=1), 1e-3)
+    assert (err <= bound).all(), (err / bound).max()
+    top2 = np.sort(ref, axis=1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > 2 * bound
+    assert decided.sum() >= (60 if precision == "fp32" else 30)
+    assert np.array_equal(y.argmax(1)[decided], ref.argmax(1)[decided])
+    if precision == "fp32":
+        assert np.array_equal(y.argmax(1), ref.argmax(1))
+
+
+def test_bf16_chunking_and_batch_split_invariance(dev):
+    m, _ = gpu_model("res15", "hardened", dev, precision="bf16")
+    ap = AudioProcessor()
+    wd = torch.from_numpy(synth.broadband(300, seed=8)).to(dev)
+    with torch.no_grad():
+        y = m.forward_wave(wd, ap)
+        m.chunk = {"fp32": 0, "bf16": 37}
+        y2 = m.forward_wave(wd, ap)
+        y3 = torch.cat([m.forward_wave(wd[:123], ap), m.forward_wave(wd[123:], ap)])
+    assert torch.allclose(y, y2, rtol=0, atol=2e-3 * float(y.abs().max())), "only the pooled-sum atomics may reorder"
+    assert torch.allclose(y, y3, rtol=0, atol=2e-3 * float(y.abs().max()))
+
+
+def test_bf16_not_available_for_cnn(dev):
+    m, _ = gpu_model("cnn-trad-fpool3", "default", dev, precision="bf16")
+    with pytest.raises(honk2_b200.NativeError):
+        m(torch.zeros(2, 101, 40, device=dev))
