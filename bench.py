@@ -170,7 +170,9 @@ def main():
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=0, help="concurrent chunk streams of the bf16 path (0 = library default)")
     ap.add_argument("--ref-batch", type=int, default=64)
+    ap.add_argument("--e2e-sub-batch", type=int, default=2048)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -179,6 +181,8 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    if args.lanes:
+        os.environ["HONK2_TC_LANES"] = str(args.lanes)
 
     import honk2_b200
     from honk2_b200 import AudioProcessor, synth
@@ -250,13 +254,12 @@ def main():
         value = B * world * K / (ms / 1e3)
 
         # ---- e2e: host buffers, copies inside the timed region
+        from honk2_b200.evaluate import HostPipeline
         host_logits = torch.empty((B, model.n_labels), dtype=torch.float32).pin_memory()
-        stage = torch.empty((B, N_SAMPLES), dtype=torch.float32, device=dev)
+        pipe = HostPipeline(model, fe, N_SAMPLES, sub_batch=args.e2e_sub_batch, device=dev)
 
         def step_e2e(i):
-            stage.copy_(host_sets[i % n_sets], non_blocking=True)
-            logits = model.forward_wave(stage, fe)
-            host_logits.copy_(logits, non_blocking=True)
+            pipe(host_sets[i % n_sets], host_logits)
 
         for i in range(2):
             step_e2e(i)

@@ -24,6 +24,7 @@
 // tile i overlaps the MMAs of tile i+1.
 #include "tc.cuh"
 #include <cuda.h>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -32,10 +33,11 @@
 namespace kws {
 
 constexpr int kTcEpiWarps = 8;
-constexpr int kTcIssuers = 4;      // MMA-issuing warps (M-tiles dealt round-robin)
-constexpr int kTcThreads = 32 * (1 + kTcIssuers + kTcEpiWarps);   // warp 0 TMA, warps 1-4 MMA, 8 epilogue warps
+constexpr int kTcIssuers = 3;      // MMA-issuing warps (M-tiles dealt round-robin)
+constexpr int kTcThreads = 32 * (1 + kTcIssuers + kTcEpiWarps);   // warp 0 TMA, warps 1-3 MMA, 8 epilogue warps
 constexpr int kTcMaxMt = 8;       // upper bound of M-tiles per tile (min(8, kAccCols / CP) at run time)
 constexpr int kAccCols = 256;     // TMEM columns per accumulator buffer
+constexpr int kTcMaxLanes = 4;
 constexpr int kMaxStages = 8;
 constexpr long long kSpinLimitCycles = 4000000000ll;
 
@@ -266,7 +268,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       }
     }
   } else if (warp <= kTcIssuers) {
-    // ================================ MMA issuers (4 warps) ================================
+    // ================================ MMA issuers (3 warps) ================================
     // A 128 x CP x 16 MMA lasts ~CP/2 tensor-pipe cycles, less than one thread needs to set up and
     // issue it, so the M-tiles of a tile are dealt round-robin to kTcIssuers warps (disjoint TMEM
     // accumulators, hence no ordering between them); every issuer commits to the same barriers.
@@ -359,19 +361,39 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       const int rows = tile_rows(tix);
       const int n_mt = tile_mt(tix);
       const int64_t utt_base = ((int64_t)b * NP) * plane_stride + (int64_t)h0 * g.W;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      for (int mt = par; mt < n_mt; mt += 2) {
+      // position of this thread in M-tile `mt`: valid flag and offset (16-byte units) inside plane 0
+      auto locate = [&](int mt, bool& valid) -> int64_t {
         const int pos = mt * 128 + q * 32 + lane;
         const int r = pos / g.Wp;
         const int w = pos - r * g.Wp - g.dpad;
-        const bool valid = (w >= 0) && (r < rows);
-        const int64_t base = utt_base + (int64_t)r * g.W + w;
+        valid = (w >= 0) && (r < rows) && (mt < n_mt);
+        return utt_base + (int64_t)r * g.W + w;
+      };
+      // The skip tensor is fetched one M-tile ahead; the first fetch is issued BEFORE waiting for
+      // the accumulators, so its latency hides behind the MMAs of this tile.
+      uint4 pv_next[HAS_PREV ? NP : 1];
+      if constexpr (HAS_PREV) {
+        bool v0;
+        const int64_t b0 = locate(par, v0);
+        if (v0) {
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) pv_next[pl] = __ldg(prev_in + b0 + pl * plane_stride);
+        }
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      for (int mt = par; mt < n_mt; mt += 2) {
+        bool valid;
+        const int64_t base = locate(mt, valid);
         uint4 pv[HAS_PREV ? NP : 1];
         if constexpr (HAS_PREV) {
-          if (valid) {
 #pragma unroll
-            for (int pl = 0; pl < NP; ++pl) pv[pl] = __ldg(prev_in + base + pl * plane_stride);
+          for (int pl = 0; pl < NP; ++pl) pv[pl] = pv_next[pl];
+          bool v2;
+          const int64_t b2 = locate(mt + 2, v2);
+          if (v2) {
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) pv_next[pl] = __ldg(prev_in + b2 + pl * plane_stride);
           }
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP;
@@ -691,6 +713,11 @@ struct TcResNet {
   float* out_w = nullptr;
   float* out_b = nullptr;
   std::map<std::tuple<const void*, int64_t, int, int, int>, CUtensorMap> maps;
+  // chunk pipelining: consecutive chunks run on `lanes` internal streams so that the prologue / tail of one
+  // chunk's layer kernels overlaps the steady state of another's (each lane has its own activation buffers)
+  int lanes = 1;
+  cudaStream_t lane_stream[kTcMaxLanes] = {};
+  cudaEvent_t ev_start = nullptr, ev_done[kTcMaxLanes] = {};
 };
 
 static int tc_max_mt(int CP) { return std::min(kTcMaxMt, kAccCols / CP); }
@@ -777,6 +804,17 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
     p->conv0_w = reinterpret_cast<float*>(b); b += round_up<size_t>(C * 9 * 4, 256);
     p->out_w = reinterpret_cast<float*>(b); b += round_up<size_t>((size_t)cfg.n_labels * C * 4, 256);
     p->out_b = reinterpret_cast<float*>(b);
+    const char* env = std::getenv("HONK2_TC_LANES");
+    p->lanes = env ? std::max(1, std::min(kTcMaxLanes, std::atoi(env))) : 2;
+    bool ok = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int l = 0; l < p->lanes && ok; ++l)
+      ok = cudaStreamCreateWithFlags(&p->lane_stream[l], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&p->ev_done[l], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+      set_error("tc_resnet_create: could not create the chunk-pipelining streams");
+      tc_resnet_destroy(p);
+      return KWS_ERR_CUDA;
+    }
   }
   *out = p;
   return KWS_OK;
@@ -785,6 +823,11 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
 void tc_resnet_destroy(TcResNet* p) {
   if (!p) return;
   if (p->blob) cudaFree(p->blob);
+  for (int l = 0; l < kTcMaxLanes; ++l) {
+    if (p->lane_stream[l]) cudaStreamDestroy(p->lane_stream[l]);
+    if (p->ev_done[l]) cudaEventDestroy(p->ev_done[l]);
+  }
+  if (p->ev_start) cudaEventDestroy(p->ev_start);
   delete p;
 }
 
@@ -839,7 +882,7 @@ size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int
   tc_map_hw(p->cfg, T, F, &H, &W);
   if (H < 1 || W < 1 || W > 256 || !tc_layers_ok(p, H, W)) return 0;
   const int64_t c = tc_chunk(p, B, H, W, chunk);
-  return 3 * round_up<size_t>((size_t)c * p->NP * H * W * 16, 1024) + round_up<size_t>((size_t)c * p->CP * 4, 1024);
+  return p->lanes * (3 * round_up<size_t>((size_t)c * p->NP * H * W * 16, 1024) + round_up<size_t>((size_t)c * p->CP * 4, 1024));
 }
 
 static int tc_get_map(TcResNet* p, const void* base, int64_t planes, int H, int W, const TcGeom& g, CUtensorMap** out) {
@@ -906,10 +949,14 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
   }
   const int64_t chunk = tc_chunk(p, B, H, W, chunk_cfg);
   const size_t buf = round_up<size_t>((size_t)chunk * p->NP * H * W * 16, 1024);
-  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws));
-  __nv_bfloat16* A[2] = {reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + buf),
-                         reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + 2 * buf)};
-  float* pool = reinterpret_cast<float*>(static_cast<char*>(ws) + 3 * buf);
+  const size_t lane_bytes = 3 * buf + round_up<size_t>((size_t)chunk * p->CP * 4, 1024);
+  // per-launch profiling needs one ordered stream; a single chunk has nothing to overlap with
+  const int lanes = (prof && prof->enabled) || B <= chunk ? 1 : p->lanes;
+  cudaStream_t caller = st;
+  if (lanes > 1) {
+    KWS_CUDA(cudaEventRecord(p->ev_start, caller));
+    for (int l = 0; l < lanes; ++l) KWS_CUDA(cudaStreamWaitEvent(p->lane_stream[l], p->ev_start, 0));
+  }
   const bool fuse_pool = c.n_layers >= 1;
   const int ph = c.pool_h > 0 ? c.pool_h : 1, pw = c.pool_w > 0 ? c.pool_w : 1;
   KWS_REQUIRE(W <= 256, "conv_0: map width %d exceeds 256", W);
@@ -921,8 +968,15 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
   const size_t smem0 = sizeof(float) * (round_up((rows0 * ph + 2) * (F + 2), 4) + p->NP * 8 * 12);
   KWS_REQUIRE(smem0 <= 48 * 1024, "conv_0: tile needs %zu bytes of shared memory", smem0);
 
-  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+  int64_t chunk_idx = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += chunk, ++chunk_idx) {
     const int64_t nb = std::min(chunk, B - b0);
+    const int lane = (int)(chunk_idx % lanes);
+    if (lanes > 1) st = p->lane_stream[lane];
+    char* lws = static_cast<char*>(ws) + (size_t)lane * lane_bytes;
+    __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(lws);
+    __nv_bfloat16* A[2] = {reinterpret_cast<__nv_bfloat16*>(lws + buf), reinterpret_cast<__nv_bfloat16*>(lws + 2 * buf)};
+    float* pool = reinterpret_cast<float*>(lws + 3 * buf);
     if (prof) prof->tick(1, st);
     if (fast0 && smem0f <= 48 * 1024)
       conv0_p8_w4_kernel<<<dim3(ceil_div(H, rows0f), (unsigned)nb), 256, smem0f, st>>>(
@@ -970,6 +1024,12 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
       tail_p8_kernel<<<(unsigned)nb, 256, 0, st>>>(x, p->out_w, p->out_b, logits + b0 * c.n_labels, c.n_maps, p->NP,
                                                    H * W, c.n_labels);
     KWS_CHECK_LAUNCH();
+  }
+  if (lanes > 1) {
+    for (int l = 0; l < lanes; ++l) {
+      KWS_CUDA(cudaEventRecord(p->ev_done[l], p->lane_stream[l]));
+      KWS_CUDA(cudaStreamWaitEvent(caller, p->ev_done[l], 0));
+    }
   }
   return KWS_OK;
 }

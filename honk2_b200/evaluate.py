@@ -61,3 +61,37 @@ def evaluate_waves(model, audio_processor, waves, targets=None, batch_size=8192,
             acc._counts = torch.zeros(2, dtype=torch.int64, device=device)
         accuracy = acc.all_reduce().get_metric()
     return full, accuracy
+
+
+class HostPipeline(object):
+    """waveforms in (pinned) HOST memory -> logits in (pinned) HOST memory, with the host->device
+    copies of sub-batch k+1 overlapped with the kernels of sub-batch k (two staging buffers, one
+    copy stream).  This is the e2e form of the collate + forward loop: the reference copies each
+    batch synchronously from pageable memory (`data.to(device)`, run/test.py:23)."""
+
+    def __init__(self, model, audio_processor, n_samples, sub_batch=2048, device=None):
+        self.model, self.ap = model, audio_processor
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.sub = int(sub_batch)
+        self.stage = [torch.empty((self.sub, n_samples), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def __call__(self, host_waves, host_logits):
+        n = host_waves.shape[0]
+        main = torch.cuda.current_stream(self.device)
+        spans = [(b0, min(n, b0 + self.sub)) for b0 in range(0, n, self.sub)]
+        with torch.no_grad():
+            for k, (b0, b1) in enumerate(spans):
+                slot = k & 1
+                with torch.cuda.stream(self.copy_stream):
+                    if k >= 2:
+                        self.copy_stream.wait_event(self.consumed[slot])    # staging buffer is free again
+                    self.stage[slot][: b1 - b0].copy_(host_waves[b0:b1], non_blocking=True)
+                    self.copied[slot].record(self.copy_stream)
+                main.wait_event(self.copied[slot])
+                logits = self.model.forward_wave(self.stage[slot][: b1 - b0], self.ap)
+                self.consumed[slot].record(main)
+                host_logits[b0:b1].copy_(logits, non_blocking=True)
+        return host_logits
