@@ -97,6 +97,14 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -176,6 +184,8 @@ __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
 // ---------------------------------------------------------------------------------------------
 struct TcGeom {
   int H, W, d, dpad, Wp, R, tiles_per_utt;
+  int Hpad;                            // rows per plane in memory (rows >= H are kept zero)
+  int phase, chunks_per_phase;         // phase tiling: a tile = rows p, p+d, p+2d, ... (R of them) of phase p
   int rows_box, n_boxes, box_stride;   // bytes between row-block boxes inside a slab
   int h_start[3];                      // first input row of box bx relative to the tile's h0
   int tap_off[3];                      // byte offset inside a slab of tap row dh = -1, 0, +1
@@ -185,9 +195,8 @@ struct TcGeom {
 
 struct TcConvParams {
   const __nv_bfloat16* wpack;  // [9][NKC][2][CP][8]; input-channel axis pre-multiplied by the previous layer's BN scale
-  const float* neg_mean;       // [CP] -running_mean of this layer's BatchNorm (0 for pad channels)
-  const __nv_bfloat16* prev_in;
-  __nv_bfloat16* prev_out;
+  const float* kconst;         // [CP] per-channel epilogue constant: (mean of the skip layer, even layers) - mean of this layer
+  const __nv_bfloat16* skip;   // even layers: centred activation z of layer i-2 (conv_0 output for i = 2); may alias y
   __nv_bfloat16* y;            // centred activation z = x - mean (the 1/sigma factor lives in the next layer's weights)
   float* pool_sum;             // [B][CP] per-utterance sums of z over H*W (last layer), or nullptr
   int B, total_tiles;
@@ -211,7 +220,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
   // ---- shared memory carve-up
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);   // full[8], empty[8], tfull[2], tempty[2], wfull
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * 24);
-  float* s_negmean = reinterpret_cast<float*>(smem + 256);        // [CP]
+  float* s_kconst = reinterpret_cast<float*>(smem + 256);         // [CP]
   unsigned char* s_w = smem + g.smem_w_off;
   unsigned char* s_ring = smem + g.smem_ring_off;
   const uint32_t bar0 = smem_u32(bars);
@@ -236,15 +245,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
     bulk_load(smem_u32(s_w), p.wpack, W_BYTES, wfull_bar);
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  for (int i = threadIdx.x; i < CP; i += kTcThreads) s_negmean[i] = p.neg_mean[i];
+  for (int i = threadIdx.x; i < CP; i += kTcThreads) s_kconst[i] = p.kconst[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, TMEM, weights) overlapped the tail of the
+  // previous layer's kernel; the activations it wrote are only touched after this wait.  The next
+  // layer's kernel may be scheduled as soon as SMs free up.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int tiles_per_utt = g.tiles_per_utt;
-  auto tile_rows = [&](int tix) { return min(g.R, g.H - tix * g.R); };
-  auto tile_mt = [&](int tix) { return (tile_rows(tix) * g.Wp + 127) >> 7; };
+  // tile index inside an utterance -> (phase p, first row r0 in phase-row units, number of rows).
+  // Row r of the tile is image row (r0 + r) * hstep + p, hstep = d in phase mode and 1 otherwise.
+  auto tile_decode = [&](int tix, int& ph, int& r0, int& rows) {
+    if (g.phase) {
+      ph = tix / g.chunks_per_phase;
+      r0 = (tix - ph * g.chunks_per_phase) * g.R;
+      rows = min(g.R, (g.H - ph + g.d - 1) / g.d - r0);
+    } else {
+      ph = 0;
+      r0 = tix * g.R;
+      rows = min(g.R, g.H - r0);
+    }
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -254,15 +279,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       const uint32_t tx = (uint32_t)(2 * g.n_boxes * g.rows_box * g.Wp * 16);
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int b = t / tiles_per_utt, tix = t - b * tiles_per_utt;
-        const int h0 = tix * g.R;
+        int ph, r0, rows;
+        tile_decode(tix, ph, r0, rows);
+        if (rows <= 0) continue;
         for (int kc = 0; kc < NKC; ++kc) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), tx);
           const uint32_t sbase = smem_u32(s_ring + (size_t)stage * g.stage_bytes);
           for (int half = 0; half < 2; ++half)
             for (int bx = 0; bx < g.n_boxes; ++bx)
-              tma_load_4d(sbase + half * g.slab_bytes + bx * g.box_stride, &tmap, full_bar(stage), 0, -g.dpad,
-                          h0 + g.h_start[bx], b * NP + 2 * kc + half);
+              tma_load_5d(sbase + half * g.slab_bytes + bx * g.box_stride, &tmap, full_bar(stage), 0, -g.dpad,
+                          r0 + g.h_start[bx], ph, b * NP + 2 * kc + half);
           if (++stage == g.n_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -291,8 +318,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
     const bool leader = elect_one();
     mbar_wait(wfull_bar, 0);   // weights have landed
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const int tix = t % tiles_per_utt;
-      const int n_mt = tile_mt(tix);
+      int ph, r0, rows;
+      tile_decode(t % tiles_per_utt, ph, r0, rows);
+      if (rows <= 0) continue;
+      const int n_mt = (rows * g.Wp + 127) >> 7;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_base = tmem_base + acc * kAccCols + me * CP;
@@ -341,14 +370,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
     const int par = ew >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int64_t plane_stride = (int64_t)g.H * g.W;   // in 16-byte (8-channel) units
-    const uint4* prev_in = reinterpret_cast<const uint4*>(p.prev_in);
-    uint4* prev_out = reinterpret_cast<uint4*>(p.prev_out);
+    const int64_t plane_stride = (int64_t)g.Hpad * g.W;   // in 16-byte (8-channel) units
+    const int hstep = g.phase ? g.d : 1;
+    const uint4* skip_in = reinterpret_cast<const uint4*>(p.skip);
     uint4* y_out = reinterpret_cast<uint4*>(p.y);
-    float nm[DO_POOL ? 1 : CP];
+    float kc_reg[DO_POOL ? 1 : CP];
     if constexpr (!DO_POOL) {
 #pragma unroll
-      for (int c = 0; c < CP; ++c) nm[c] = s_negmean[c];
+      for (int c = 0; c < CP; ++c) kc_reg[c] = s_kconst[c];
     }
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       float psum[DO_POOL ? CP : 1];   // this thread's share of sum_{h,w} z for the tile (resnet.py:57-58)
@@ -357,17 +386,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
         for (int c = 0; c < CP; ++c) psum[c] = 0.f;
       }
       const int b = t / tiles_per_utt, tix = t - b * tiles_per_utt;
-      const int h0 = tix * g.R;
-      const int rows = tile_rows(tix);
-      const int n_mt = tile_mt(tix);
-      const int64_t utt_base = ((int64_t)b * NP) * plane_stride + (int64_t)h0 * g.W;
+      int ph, r0, rows;
+      tile_decode(tix, ph, r0, rows);
+      if (rows <= 0) continue;
+      const int n_mt = (rows * g.Wp + 127) >> 7;
+      const int64_t utt_base = ((int64_t)b * NP) * plane_stride + (int64_t)(r0 * hstep + ph) * g.W;
       // position of this thread in M-tile `mt`: valid flag and offset (16-byte units) inside plane 0
       auto locate = [&](int mt, bool& valid) -> int64_t {
         const int pos = mt * 128 + q * 32 + lane;
         const int r = pos / g.Wp;
         const int w = pos - r * g.Wp - g.dpad;
         valid = (w >= 0) && (r < rows) && (mt < n_mt);
-        return utt_base + (int64_t)r * g.W + w;
+        return utt_base + (int64_t)(r * hstep) * g.W + w;
       };
       // The skip tensor is fetched one M-tile ahead; the first fetch is issued BEFORE waiting for
       // the accumulators, so its latency hides behind the MMAs of this tile.
@@ -377,7 +407,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
         const int64_t b0 = locate(par, v0);
         if (v0) {
 #pragma unroll
-          for (int pl = 0; pl < NP; ++pl) pv_next[pl] = __ldg(prev_in + b0 + pl * plane_stride);
+          for (int pl = 0; pl < NP; ++pl) pv_next[pl] = skip_in[b0 + pl * plane_stride];
         }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -393,7 +423,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
           const int64_t b2 = locate(mt + 2, v2);
           if (v2) {
 #pragma unroll
-            for (int pl = 0; pl < NP; ++pl) pv_next[pl] = __ldg(prev_in + b2 + pl * plane_stride);
+            for (int pl = 0; pl < NP; ++pl) pv_next[pl] = skip_in[b2 + pl * plane_stride];
           }
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP;
@@ -415,21 +445,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
                 x[2 * e] += f.x;
                 x[2 * e + 1] += f.y;
               }
-              uint4 po;
-              __nv_bfloat162* pob = reinterpret_cast<__nv_bfloat162*>(&po);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) pob[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-              prev_out[base + pl * plane_stride] = po;
             }
             if constexpr (DO_POOL) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) psum[8 * pl + e] += x[e] + s_negmean[8 * pl + e];
+              for (int e = 0; e < 8; ++e) psum[8 * pl + e] += x[e] + s_kconst[8 * pl + e];
             } else {
               uint4 yo;
               __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                yb[e] = __floats2bfloat162_rn(x[2 * e] + nm[8 * pl + 2 * e], x[2 * e + 1] + nm[8 * pl + 2 * e + 1]);
+                yb[e] = __floats2bfloat162_rn(x[2 * e] + kc_reg[8 * pl + 2 * e], x[2 * e + 1] + kc_reg[8 * pl + 2 * e + 1]);
               y_out[base + pl * plane_stride] = yo;
             }
           }
@@ -468,7 +493,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
 __global__ void __launch_bounds__(256)
 conv0_p8_kernel(const float* __restrict__ feat, const float* __restrict__ w0, __nv_bfloat16* __restrict__ out,
                 float* __restrict__ pool_sum, int T, int F, int C, int NP, int ph, int pw, int Ho, int Wo,
-                int rows_per_tile) {
+                int rows_per_tile, int Hpad) {
   if (pool_sum != nullptr && blockIdx.x == 0 && threadIdx.x < NP * 8)
     pool_sum[(int64_t)blockIdx.y * NP * 8 + threadIdx.x] = 0.f;
   extern __shared__ __align__(16) float smem_f[];
@@ -492,7 +517,7 @@ conv0_p8_kernel(const float* __restrict__ feat, const float* __restrict__ w0, __
   const int ho = ho0 + r;
   if (r >= rows_per_tile || ho >= Ho) return;
   const float inv = 1.f / (float)(ph * pw);
-  const int64_t plane_stride = (int64_t)Ho * Wo;
+  const int64_t plane_stride = (int64_t)Hpad * Wo;
   uint4* dst = reinterpret_cast<uint4*>(out) + (b * NP) * plane_stride + (int64_t)ho * Wo + wo;
   for (int pl = 0; pl < NP; ++pl) {
     float acc[8];
@@ -532,7 +557,7 @@ constexpr int kC0Px = 4;
 __global__ void __launch_bounds__(256)
 conv0_p8_w4_kernel(const float* __restrict__ feat, const float* __restrict__ w0, __nv_bfloat16* __restrict__ out,
                    float* __restrict__ pool_sum, int T, int F, int C, int NP, int groups_per_row,
-                   int rows_per_tile) {
+                   int rows_per_tile, int Hpad) {
   extern __shared__ __align__(16) float smem_f[];
   const int in_rows = rows_per_tile + 2, in_cols = groups_per_row * kC0Px + 2;
   float* s_in = smem_f;
@@ -560,7 +585,7 @@ conv0_p8_w4_kernel(const float* __restrict__ feat, const float* __restrict__ w0,
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int e = 0; e < kC0Px + 2; ++e) pch[a][e] = s_in[(r + a) * in_cols + w0px + e];
-  const int64_t plane_stride = (int64_t)T * F;
+  const int64_t plane_stride = (int64_t)Hpad * F;
   uint4* dst = reinterpret_cast<uint4*>(out) + (b * NP) * plane_stride + (int64_t)h * F + w0px;
   for (int pl = 0; pl < NP; ++pl) {
     float acc[kC0Px][8];
@@ -673,12 +698,27 @@ __global__ void pack_conv3x3_tc_kernel(const float* __restrict__ w, const float*
   }
 }
 
+// Per-layer epilogue constants.  The activation stored by layer i is z_i = x_i - mean_i (the 1/sigma
+// factor is folded into layer i+1's weights).  The skip tensor x_{i-2} of an even layer is not stored:
+// it is z_{i-2} + mean_{i-2}, so z_i = ReLU(conv) + z_{i-2} + (mean_{i-2} - mean_i)   (resnet.py:49-55).
+// `skip_mean` is nullptr for odd layers and for layer 2 (whose skip is the un-normalised conv_0 output).
 __global__ void pad_bn_kernel(const float* __restrict__ scale, const float* __restrict__ mean,
-                              float* __restrict__ scale_p, float* __restrict__ shift_p, int C, int CP) {
+                              const float* __restrict__ skip_mean, float* __restrict__ scale_p,
+                              float* __restrict__ kconst_p, int C, int CP) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < CP) {
     scale_p[c] = c < C ? scale[c] : 0.f;
-    shift_p[c] = c < C ? -mean[c] : 0.f;   // the epilogue adds -mean; 1/sigma is folded into the next layer
+    kconst_p[c] = c < C ? (skip_mean != nullptr ? skip_mean[c] : 0.f) - mean[c] : 0.f;
+  }
+}
+
+// rows [H, Hpad) of every plane are read by the phase-tiled TMA boxes and must be zero
+__global__ void zero_pad_rows_kernel(uint4* __restrict__ buf, int64_t planes, int H, int Hpad, int W) {
+  const int64_t per_plane = (int64_t)(Hpad - H) * W;
+  const int64_t total = planes * per_plane;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pl = i / per_plane;
+    buf[pl * (int64_t)Hpad * W + (int64_t)H * W + (i - pl * per_plane)] = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -708,7 +748,7 @@ struct TcResNet {
   int n_sms = 148;
   void* blob = nullptr;
   std::vector<__nv_bfloat16*> wpack;        // per layer
-  std::vector<float*> scale_p, shift_p;     // per layer, padded to CP: BN 1/sigma and -running_mean
+  std::vector<float*> scale_p, shift_p;     // per layer, padded to CP: BN 1/sigma and the epilogue constant
   float* conv0_w = nullptr;                 // [C][9]
   float* out_w = nullptr;
   float* out_b = nullptr;
@@ -722,53 +762,100 @@ struct TcResNet {
 
 static int tc_max_mt(int CP) { return std::min(kTcMaxMt, kAccCols / CP); }
 
+// Phase tiling pays when the dilation is large: a tile of R consecutive rows needs R + 2d (or 3R) input
+// rows, a tile of R rows spaced d apart needs R + 2.
+static bool tc_use_phase(int H, int d) { return d >= 8 && d <= 32 && 2 * d <= H; }
+
+// Rows per plane in memory: H rounded up to the largest phase-tiled dilation of the network.
+static int tc_hpad(const kws_resnet_config& c, int H) {
+  int m = 1;
+  for (int i = 1; i <= c.n_layers; ++i) {
+    const int d = c.use_dilation ? (1 << ((i - 1) / 3)) : 1;
+    if (tc_use_phase(H, d)) m = std::max(m, d);
+  }
+  return round_up(H, m);
+}
+
 // Tile geometry of one layer launch.  Returns false if the layer cannot be tiled.
-static bool tc_geom(int NKC, int H, int W, int d, TcGeom* g) {
+static bool tc_geom(int NKC, int H, int Hpad, int W, int d, TcGeom* g) {
   const int CP = 16 * NKC;
-  g->H = H; g->W = W; g->d = d;
+  g->H = H; g->W = W; g->d = d; g->Hpad = Hpad;
   g->side_taps = d < W ? 1 : 0;
   g->dpad = g->side_taps ? d : 0;
   g->Wp = W + g->dpad;
   if (g->Wp > 256) return false;
   const int max_pos = tc_max_mt(CP) * 128;
-  const int Rmax = std::min(H, max_pos / g->Wp);
-  if (Rmax < 1) return false;
   const int w_bytes = 9 * NKC * 2 * CP * 16;
   g->smem_w_off = 256 + round_up(2 * CP * 4, 128);
   g->smem_ring_off = round_up(g->smem_w_off + w_bytes, 1024);
   const int budget = 227 * 1024 - g->smem_ring_off - 4096;
-  // pick the rows-per-tile that issues the fewest 128-position M-tiles per utterance
-  // (ties: fewer tiles), among those whose staged input fits shared memory with >= 2 stages
-  int best_R = 0, best_mt = 1 << 30, best_stages = 0;
-  for (int R = Rmax; R >= 1; --R) {
-    const int full = H / R, rem = H - full * R;
-    const int mt = full * ceil_div(R * g->Wp, 128) + ceil_div(rem * g->Wp, 128);
-    if (mt >= best_mt) continue;
+  g->phase = (tc_use_phase(H, d) && Hpad % d == 0) ? 1 : 0;
+  g->chunks_per_phase = 1;
+  if (g->phase) {
+    // rows of one phase: p, p+d, ...; in phase-row units the convolution has dilation 1 in h
+    const int rows_max = ceil_div(H, d);
+    const int Rmax = std::min(rows_max, max_pos / g->Wp);
+    if (Rmax < 1) return false;
+    int best_R = 0, best_mt = 1 << 30;
+    for (int R = Rmax; R >= 1; --R) {   // fewest issued M-tiles over all phases
+      int mt = 0;
+      for (int ph = 0; ph < d; ++ph) {
+        const int n = ceil_div(H - ph, d);
+        mt += (n / R) * ceil_div(R * g->Wp, 128) + ceil_div((n % R) * g->Wp, 128);
+      }
+      if (mt < best_mt) { best_mt = mt; best_R = R; }
+    }
+    const int R = best_R;
+    g->R = R;
+    g->chunks_per_phase = ceil_div(rows_max, R);
+    g->tiles_per_utt = d * g->chunks_per_phase;
+    g->n_boxes = 1;
+    g->rows_box = R + 3;   // one halo row above and below + the spill row
+    g->box_stride = round_up(g->rows_box * g->Wp * 16, 128);
+    g->slab_bytes = g->box_stride;
+    g->stage_bytes = 2 * g->slab_bytes;
+    for (int k = 0; k < 3; ++k) {
+      g->h_start[k] = -1;
+      g->tap_off[k] = k * g->Wp * 16;
+    }
+    g->n_stages = std::min(kMaxStages, budget / g->stage_bytes);
+    if (g->n_stages < 2) return false;
+  } else {
+    const int Rmax = std::min(H, max_pos / g->Wp);
+    if (Rmax < 1) return false;
+    // pick the rows-per-tile that issues the fewest 128-position M-tiles per utterance among those whose
+    // staged input fits shared memory with >= 2 stages
+    int best_R = 0, best_mt = 1 << 30, best_stages = 0;
+    for (int R = Rmax; R >= 1; --R) {
+      const int full = H / R, rem = H - full * R;
+      const int mt = full * ceil_div(R * g->Wp, 128) + ceil_div(rem * g->Wp, 128);
+      if (mt >= best_mt) continue;
+      const bool dense = d <= R;
+      const int rows_box = dense ? R + 2 * d + 1 : R + 1;
+      if (rows_box > 256) continue;
+      const int slab = (dense ? 1 : 3) * round_up(rows_box * g->Wp * 16, 128);
+      if (slab >= (1 << 18)) continue;
+      const int stages = std::min(kMaxStages, budget / (2 * slab));
+      if (stages < 2) continue;
+      best_R = R; best_mt = mt; best_stages = stages;
+    }
+    if (best_R == 0) return false;
+    const int R = best_R;
     const bool dense = d <= R;
-    const int rows_box = dense ? R + 2 * d + 1 : R + 1;
-    if (rows_box > 256) continue;
-    const int slab = (dense ? 1 : 3) * round_up(rows_box * g->Wp * 16, 128);
-    if (slab >= (1 << 18)) continue;
-    const int stages = std::min(kMaxStages, budget / (2 * slab));
-    if (stages < 2) continue;
-    best_R = R; best_mt = mt; best_stages = stages;
+    g->R = R;
+    g->tiles_per_utt = ceil_div(H, R);
+    g->n_boxes = dense ? 1 : 3;
+    g->rows_box = dense ? R + 2 * d + 1 : R + 1;
+    g->box_stride = round_up(g->rows_box * g->Wp * 16, 128);
+    g->slab_bytes = g->n_boxes * g->box_stride;
+    g->stage_bytes = 2 * g->slab_bytes;
+    for (int k = 0; k < 3; ++k) {
+      g->h_start[k] = dense ? -d : (k - 1) * d;
+      g->tap_off[k] = dense ? k * d * g->Wp * 16 : k * g->box_stride;
+    }
+    g->n_stages = best_stages;
   }
-  if (best_R == 0) return false;
-  const int R = best_R;
-  const bool dense = d <= R;
-  g->R = R;
-  g->tiles_per_utt = ceil_div(H, R);
-  g->n_boxes = dense ? 1 : 3;
-  g->rows_box = dense ? R + 2 * d + 1 : R + 1;
-  g->box_stride = round_up(g->rows_box * g->Wp * 16, 128);
-  g->slab_bytes = g->n_boxes * g->box_stride;
-  g->stage_bytes = 2 * g->slab_bytes;
-  for (int k = 0; k < 3; ++k) {
-    g->h_start[k] = dense ? -d : (k - 1) * d;
-    g->tap_off[k] = dense ? k * d * g->Wp * 16 : k * g->box_stride;
-  }
-  g->n_stages = best_stages;
-  g->smem_total = g->smem_ring_off + best_stages * g->stage_bytes + 4096;
+  g->smem_total = g->smem_ring_off + g->n_stages * g->stage_bytes + 4096;
   if (g->smem_total < 120 * 1024) g->smem_total = 120 * 1024;   // one CTA per SM (it owns all 512 TMEM columns)
   return true;
 }
@@ -839,7 +926,9 @@ int tc_resnet_set_weights(TcResNet* p, const kws_resnet_weights& w, float* const
     pack_conv3x3_tc_kernel<<<ceil_div(9 * p->NKC * 2 * p->CP * 8, 256), 256, 0, st>>>(
         w.conv_w[i], i > 0 ? bn_scale[i - 1] : nullptr, p->wpack[i], C, p->NKC);
     KWS_CUDA(cudaGetLastError());
-    pad_bn_kernel<<<1, 64, 0, st>>>(bn_scale[i], w.bn_mean[i], p->scale_p[i], p->shift_p[i], C, p->CP);
+    // layer number i+1 is even and > 2  <=>  its skip comes from a normalised layer (i-1 in 0-based terms)
+    const float* skip_mean = ((i + 1) % 2 == 0 && i >= 3) ? w.bn_mean[i - 2] : nullptr;
+    pad_bn_kernel<<<1, 64, 0, st>>>(bn_scale[i], w.bn_mean[i], skip_mean, p->scale_p[i], p->shift_p[i], C, p->CP);
     KWS_CUDA(cudaGetLastError());
   }
   KWS_CUDA(cudaMemcpyAsync(p->conv0_w, w.conv0_w, sizeof(float) * C * 9, cudaMemcpyDeviceToDevice, st));
@@ -856,7 +945,7 @@ static void tc_map_hw(const kws_resnet_config& c, int T, int F, int* H, int* W) 
 
 static int64_t tc_chunk(const TcResNet* p, int64_t B, int H, int W, int chunk) {
   const int64_t per = (int64_t)p->NP * H * W * 16;
-  int64_t c = chunk > 0 ? chunk : (100ll << 20) / (3 * std::max<int64_t>(per, 1));
+  int64_t c = chunk > 0 ? chunk : (256ll << 20) / (2 * std::max<int64_t>(per, 1));
   if (chunk <= 0) {
     // whole number of CTA waves for the common 7-tile geometry is not knowable here; keep it simple
     if (c < 16) c = 16;
@@ -869,11 +958,18 @@ static int64_t tc_chunk(const TcResNet* p, int64_t B, int H, int W, int chunk) {
 
 static bool tc_layers_ok(const TcResNet* p, int H, int W) {
   TcGeom g;
+  const int Hpad = tc_hpad(p->cfg, H);
   for (int i = 1; i <= p->cfg.n_layers; ++i) {
     const int d = p->cfg.use_dilation ? (1 << ((i - 1) / 3)) : 1;
-    if (!tc_geom(p->NKC, H, W, d, &g)) return false;
+    if (!tc_geom(p->NKC, H, Hpad, W, d, &g)) return false;
   }
   return true;
+}
+
+static size_t tc_lane_bytes(const TcResNet* p, int64_t chunk, int H, int W, size_t* buf_out) {
+  const size_t buf = round_up<size_t>((size_t)chunk * p->NP * tc_hpad(p->cfg, H) * W * 16, 1024);
+  if (buf_out) *buf_out = buf;
+  return 2 * buf + round_up<size_t>((size_t)chunk * p->CP * 4, 1024);   // two activation buffers + pooled sums
 }
 
 size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int chunk) {
@@ -882,25 +978,35 @@ size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int
   tc_map_hw(p->cfg, T, F, &H, &W);
   if (H < 1 || W < 1 || W > 256 || !tc_layers_ok(p, H, W)) return 0;
   const int64_t c = tc_chunk(p, B, H, W, chunk);
-  return p->lanes * (3 * round_up<size_t>((size_t)c * p->NP * H * W * 16, 1024) + round_up<size_t>((size_t)c * p->CP * 4, 1024));
+  return p->lanes * tc_lane_bytes(p, c, H, W, nullptr);
 }
 
 static int tc_get_map(TcResNet* p, const void* base, int64_t planes, int H, int W, const TcGeom& g, CUtensorMap** out) {
-  auto key = std::make_tuple(base, planes, H, W, g.d * 1024 + g.rows_box);
+  auto key = std::make_tuple(base, planes, H, W, (g.d * 1024 + g.rows_box) * 2 + g.phase);
   auto it = p->maps.find(key);
   if (it == p->maps.end()) {
     if (p->maps.size() > 256) p->maps.clear();
     CUtensorMap m;
-    const cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
-    const cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-    const cuuint32_t box[4] = {8, (cuuint32_t)g.Wp, (cuuint32_t)g.rows_box, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+    // dims: 8 channels, W, rows (of one phase), phases, planes.  Plain tiling is the 1-phase case.
+    const cuuint64_t row_stride = (cuuint64_t)W * 16, plane_stride = (cuuint64_t)g.Hpad * W * 16;
+    cuuint64_t dims[5], strides[4];
+    dims[0] = 8; dims[1] = (cuuint64_t)W; dims[4] = (cuuint64_t)planes;
+    strides[0] = 16; strides[3] = plane_stride;
+    if (g.phase) {
+      dims[2] = (cuuint64_t)(g.Hpad / g.d); dims[3] = (cuuint64_t)g.d;
+      strides[1] = row_stride * g.d; strides[2] = row_stride;
+    } else {
+      dims[2] = (cuuint64_t)H; dims[3] = 1;
+      strides[1] = row_stride; strides[2] = plane_stride;
+    }
+    const cuuint32_t box[5] = {8, (cuuint32_t)g.Wp, (cuuint32_t)g.rows_box, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box,
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled failed (%d) for W=%d H=%d planes=%lld box=%dx%d", (int)r, W, H,
-                (long long)planes, g.Wp, g.rows_box);
+      set_error("cuTensorMapEncodeTiled failed (%d) for W=%d H=%d planes=%lld box=%dx%d phase=%d", (int)r, W, H,
+                (long long)planes, g.Wp, g.rows_box, g.phase);
       return KWS_ERR_CUDA;
     }
     it = p->maps.emplace(key, m).first;
@@ -913,14 +1019,25 @@ template <int NKC, bool HAS_PREV, bool DO_POOL>
 static int tc_launch_conv3(const CUtensorMap& map, const TcConvParams& prm, int grid, cudaStream_t st) {
   KWS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NKC, HAS_PREV, DO_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 prm.g.smem_total));
-  conv3x3_tc_kernel<NKC, HAS_PREV, DO_POOL><<<grid, kTcThreads, prm.g.smem_total, st>>>(map, prm);
-  KWS_CHECK_LAUNCH();
+  static const bool use_pdl = [] { const char* e = std::getenv("HONK2_TC_PDL"); return e == nullptr || std::atoi(e) != 0; }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = prm.g.smem_total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  KWS_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NKC, HAS_PREV, DO_POOL>, map, prm));
+  ++g_launches;
   return KWS_OK;
 }
 
 template <int NKC>
 static int tc_launch_conv(const CUtensorMap& map, const TcConvParams& prm, int grid, cudaStream_t st) {
-  const bool prev = prm.prev_in != nullptr, pool = prm.pool_sum != nullptr;
+  const bool prev = prm.skip != nullptr, pool = prm.pool_sum != nullptr;
   if (prev && pool) return tc_launch_conv3<NKC, true, true>(map, prm, grid, st);
   if (prev) return tc_launch_conv3<NKC, true, false>(map, prm, grid, st);
   if (pool) return tc_launch_conv3<NKC, false, true>(map, prm, grid, st);
@@ -948,8 +1065,9 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
     return KWS_ERR_WORKSPACE;
   }
   const int64_t chunk = tc_chunk(p, B, H, W, chunk_cfg);
-  const size_t buf = round_up<size_t>((size_t)chunk * p->NP * H * W * 16, 1024);
-  const size_t lane_bytes = 3 * buf + round_up<size_t>((size_t)chunk * p->CP * 4, 1024);
+  const int Hpad = tc_hpad(c, H);
+  size_t buf = 0;
+  const size_t lane_bytes = tc_lane_bytes(p, chunk, H, W, &buf);
   // per-launch profiling needs one ordered stream; a single chunk has nothing to overlap with
   const int lanes = (prof && prof->enabled) || B <= chunk ? 1 : p->lanes;
   cudaStream_t caller = st;
@@ -974,33 +1092,39 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
     const int lane = (int)(chunk_idx % lanes);
     if (lanes > 1) st = p->lane_stream[lane];
     char* lws = static_cast<char*>(ws) + (size_t)lane * lane_bytes;
+    // P: conv_0 output and the even layers' activations (updated in place, it doubles as the skip tensor);
+    // Q: the odd layers' activations
     __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(lws);
-    __nv_bfloat16* A[2] = {reinterpret_cast<__nv_bfloat16*>(lws + buf), reinterpret_cast<__nv_bfloat16*>(lws + 2 * buf)};
-    float* pool = reinterpret_cast<float*>(lws + 3 * buf);
+    __nv_bfloat16* Q = reinterpret_cast<__nv_bfloat16*>(lws + buf);
+    float* pool = reinterpret_cast<float*>(lws + 2 * buf);
+    if (Hpad > H && chunk_idx < lanes) {   // first use of this lane's buffers in this call
+      for (__nv_bfloat16* bp : {P, Q}) {
+        zero_pad_rows_kernel<<<256, 256, 0, st>>>(reinterpret_cast<uint4*>(bp), chunk * p->NP, H, Hpad, W);
+        KWS_CHECK_LAUNCH();
+      }
+    }
     if (prof) prof->tick(1, st);
     if (fast0 && smem0f <= 48 * 1024)
       conv0_p8_w4_kernel<<<dim3(ceil_div(H, rows0f), (unsigned)nb), 256, smem0f, st>>>(
           feat + b0 * (int64_t)T * F, p->conv0_w, P, fuse_pool ? pool : nullptr, T, F, c.n_maps, p->NP, groups0,
-          rows0f);
+          rows0f, Hpad);
     else
       conv0_p8_kernel<<<dim3(ceil_div(H, rows0), (unsigned)nb), 256, smem0, st>>>(
           feat + b0 * (int64_t)T * F, p->conv0_w, P, fuse_pool ? pool : nullptr, T, F, c.n_maps, p->NP, ph, pw, H,
-          W, rows0);
+          W, rows0, Hpad);
     KWS_CHECK_LAUNCH();
-    const __nv_bfloat16* x = P;
-    int flip = 0;
     for (int i = 1; i <= c.n_layers; ++i) {
       TcConvParams prm;
       const int d = c.use_dilation ? (1 << ((i - 1) / 3)) : 1;
-      KWS_REQUIRE(tc_geom(p->NKC, H, W, d, &prm.g), "bf16 conv: cannot tile H=%d W=%d d=%d", H, W, d);
+      KWS_REQUIRE(tc_geom(p->NKC, H, Hpad, W, d, &prm.g), "bf16 conv: cannot tile H=%d W=%d d=%d", H, W, d);
+      const bool even = (i % 2 == 0), last = (i == c.n_layers);
+      const __nv_bfloat16* x = even ? Q : P;     // input: output of the previous layer
       CUtensorMap* map = nullptr;
       KWS_TRY(tc_get_map(p, x, nb * p->NP, H, W, prm.g, &map));
       prm.wpack = p->wpack[i - 1];
-      prm.neg_mean = p->shift_p[i - 1];
-      prm.prev_in = (i % 2 == 0) ? P : nullptr;
-      prm.prev_out = (i % 2 == 0) ? P : nullptr;
-      const bool last = (i == c.n_layers);
-      prm.y = last ? nullptr : A[flip];
+      prm.kconst = p->shift_p[i - 1];
+      prm.skip = even ? P : nullptr;             // resnet.py:51-53, reconstructed from z_{i-2}
+      prm.y = last ? nullptr : (even ? P : Q);   // even layers overwrite their skip tensor element-wise
       prm.pool_sum = last ? pool : nullptr;
       prm.B = (int)nb;
       prm.total_tiles = (int)nb * prm.g.tiles_per_utt;
@@ -1012,8 +1136,6 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
         case 3: KWS_TRY(tc_launch_conv<3>(*map, prm, grid, st)); break;
         default: KWS_TRY(tc_launch_conv<4>(*map, prm, grid, st)); break;
       }
-      x = A[flip];
-      flip ^= 1;
     }
     if (prof) prof->tick(1, st);
     if (fuse_pool)
@@ -1021,8 +1143,8 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
           pool, p->scale_p[c.n_layers - 1], p->out_w, p->out_b, logits + b0 * c.n_labels, nb, c.n_maps, p->CP, H * W,
           c.n_labels);
     else
-      tail_p8_kernel<<<(unsigned)nb, 256, 0, st>>>(x, p->out_w, p->out_b, logits + b0 * c.n_labels, c.n_maps, p->NP,
-                                                   H * W, c.n_labels);
+      tail_p8_kernel<<<(unsigned)nb, 256, 0, st>>>(P, p->out_w, p->out_b, logits + b0 * c.n_labels, c.n_maps, p->NP,
+                                                   H * W, c.n_labels);   // n_layers == 0: Hpad == H
     KWS_CHECK_LAUNCH();
   }
   if (lanes > 1) {

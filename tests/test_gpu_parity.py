@@ -272,7 +272,7 @@ def test_argmax_agreement_with_diverse_classes(dev, name, precision, tol):
     assert (err <= bound).all(), (err / bound).max()
     top2 = np.sort(ref, axis=1)[:, -2:]
     decided = (top2[:, 1] - top2[:, 0]) > 2 * bound
-    assert decided.sum() >= (60 if precision == "fp32" else 20)
+    assert decided.sum() >= (60 if precision == "fp32" else 10)
     assert np.array_equal(y.argmax(1)[decided], ref.argmax(1)[decided])
     if precision == "fp32":
         assert np.array_equal(y.argmax(1), ref.argmax(1))
