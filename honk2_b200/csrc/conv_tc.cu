@@ -257,6 +257,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int tiles_per_utt = g.tiles_per_utt;
+  // Each CTA takes a contiguous range of tiles: consecutive tiles of one utterance stay on one SM (L2/TLB
+  // locality, and the fused pooling flushes once per utterance instead of once per tile).
+  const int t_begin = (int)(((int64_t)blockIdx.x * p.total_tiles) / gridDim.x);
+  const int t_end = (int)(((int64_t)(blockIdx.x + 1) * p.total_tiles) / gridDim.x);
   // tile index inside an utterance -> (phase p, first row r0 in phase-row units, number of rows).
   // Row r of the tile is image row (r0 + r) * hstep + p, hstep = d in phase mode and 1 otherwise.
   auto tile_decode = [&](int tix, int& ph, int& r0, int& rows) {
@@ -277,7 +281,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (uint32_t)(2 * g.n_boxes * g.rows_box * g.Wp * 16);
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = t_begin; t < t_end; ++t) {
         const int b = t / tiles_per_utt, tix = t - b * tiles_per_utt;
         int ph, r0, rows;
         tile_decode(tix, ph, r0, rows);
@@ -317,7 +321,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
     const int first_tap = side ? 0 : 1;
     const bool leader = elect_one();
     mbar_wait(wfull_bar, 0);   // weights have landed
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = t_begin; t < t_end; ++t) {
       int ph, r0, rows;
       tile_decode(t % tiles_per_utt, ph, r0, rows);
       if (rows <= 0) continue;
@@ -379,13 +383,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
 #pragma unroll
       for (int c = 0; c < CP; ++c) kc_reg[c] = s_kconst[c];
     }
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      float psum[DO_POOL ? CP : 1];   // this thread's share of sum_{h,w} z for the tile (resnet.py:57-58)
+    float psum[DO_POOL ? CP : 1];   // this thread's share of sum_{h,w} z of the current utterance (resnet.py:57-58)
+    int pool_b = -1;
+    auto pool_flush = [&]() {
       if constexpr (DO_POOL) {
+        if (pool_b >= 0) {   // warp-reduce the 32 positions, one atomic per channel
+#pragma unroll
+          for (int c = 0; c < CP; ++c) {
+            float sum = psum[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == (c & 31)) atomicAdd(p.pool_sum + (int64_t)pool_b * CP + c, sum);
+          }
+        }
 #pragma unroll
         for (int c = 0; c < CP; ++c) psum[c] = 0.f;
       }
+    };
+    pool_flush();
+    for (int t = t_begin; t < t_end; ++t) {
       const int b = t / tiles_per_utt, tix = t - b * tiles_per_utt;
+      if (DO_POOL && b != pool_b) { pool_flush(); pool_b = b; }
       int ph, r0, rows;
       tile_decode(tix, ph, r0, rows);
       if (rows <= 0) continue;
@@ -465,17 +483,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-      if constexpr (DO_POOL) {
-        // the tile belongs to one utterance: warp-reduce the 32 positions, one atomic per channel
-#pragma unroll
-        for (int c = 0; c < CP; ++c) {
-          float sum = psum[c];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == (c & 31)) atomicAdd(p.pool_sum + (int64_t)b * CP + c, sum);
-        }
-      }
     }
+    pool_flush();
   }
 
   // ---- teardown

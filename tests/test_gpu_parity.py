@@ -234,7 +234,11 @@ def test_bf16_logits_vs_reference_golden(dev, name, variant, model_golden):
     ref = model_golden[f"{name}/{variant}/logits"]
     assert np.isfinite(y).all()
     assert logit_err(y, ref) <= BF16_TOL, (name, variant, logit_err(y, ref))
-    assert np.array_equal(y.argmax(1), ref.argmax(1))
+    # argmax must agree wherever the reference's top-2 margin exceeds twice the bf16 error bound
+    bound = BF16_TOL * np.maximum(np.abs(ref).max(axis=1), 1e-3)
+    top2 = np.sort(ref, axis=1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > 2 * bound
+    assert np.array_equal(y.argmax(1)[decided], ref.argmax(1)[decided])
 
 
 def _calibrated(name, dev, n_cal=48, seed=21):
