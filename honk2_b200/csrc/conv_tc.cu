@@ -110,6 +110,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -496,6 +497,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
   }
 }
 
+}  // namespace kws
+#include "resnet_fused.cuh"
+namespace kws {
+
 // ---------------------------------------------------------------------------------------------
 // conv_0 (1 -> C, 3x3, pad 1) + ReLU + AvgPool -> planar-8 bf16 (resnet.py:40-44).
 // One thread per output pixel; channels in groups of 8 -> one 16-byte store per plane.
@@ -762,6 +767,13 @@ struct TcResNet {
   float* out_w = nullptr;
   float* out_b = nullptr;
   std::map<std::tuple<const void*, int64_t, int, int, int>, CUtensorMap> maps;
+  // whole-network persistent kernel (resnet_fused.cuh): device copies of the layer table and tensor maps,
+  // rebuilt when the input shape or the workspace changes
+  bool fused_enabled = true;
+  void* fused_dev = nullptr;   // [TcLayerDesc x n_layers][pad][CUtensorMap x n_layers]
+  std::tuple<int, int, const void*> fused_key{-1, -1, nullptr};
+  TcFusedParams fused_prm{};
+  int fused_smem = 0;
   // chunk pipelining: consecutive chunks run on `lanes` internal streams so that the prologue / tail of one
   // chunk's layer kernels overlaps the steady state of another's (each lane has its own activation buffers)
   int lanes = 1;
@@ -900,6 +912,8 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
     p->conv0_w = reinterpret_cast<float*>(b); b += round_up<size_t>(C * 9 * 4, 256);
     p->out_w = reinterpret_cast<float*>(b); b += round_up<size_t>((size_t)cfg.n_labels * C * 4, 256);
     p->out_b = reinterpret_cast<float*>(b);
+    const char* fenv = std::getenv("HONK2_TC_FUSED");
+    p->fused_enabled = fenv == nullptr || std::atoi(fenv) != 0;
     const char* env = std::getenv("HONK2_TC_LANES");
     p->lanes = env ? std::max(1, std::min(kTcMaxLanes, std::atoi(env))) : 2;
     bool ok = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) == cudaSuccess;
@@ -919,6 +933,7 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
 void tc_resnet_destroy(TcResNet* p) {
   if (!p) return;
   if (p->blob) cudaFree(p->blob);
+  if (p->fused_dev) cudaFree(p->fused_dev);
   for (int l = 0; l < kTcMaxLanes; ++l) {
     if (p->lane_stream[l]) cudaStreamDestroy(p->lane_stream[l]);
     if (p->ev_done[l]) cudaEventDestroy(p->ev_done[l]);
@@ -981,14 +996,7 @@ static size_t tc_lane_bytes(const TcResNet* p, int64_t chunk, int H, int W, size
   return 2 * buf + round_up<size_t>((size_t)chunk * p->CP * 4, 1024);   // two activation buffers + pooled sums
 }
 
-size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int chunk) {
-  if (!p || !p->supported) return 0;
-  int H, W;
-  tc_map_hw(p->cfg, T, F, &H, &W);
-  if (H < 1 || W < 1 || W > 256 || !tc_layers_ok(p, H, W)) return 0;
-  const int64_t c = tc_chunk(p, B, H, W, chunk);
-  return p->lanes * tc_lane_bytes(p, c, H, W, nullptr);
-}
+static int tc_encode_map(const void* base, int64_t planes, int H, int W, const TcGeom& g, CUtensorMap* out);
 
 static int tc_get_map(TcResNet* p, const void* base, int64_t planes, int H, int W, const TcGeom& g, CUtensorMap** out) {
   auto key = std::make_tuple(base, planes, H, W, (g.d * 1024 + g.rows_box) * 2 + g.phase);
@@ -996,6 +1004,17 @@ static int tc_get_map(TcResNet* p, const void* base, int64_t planes, int H, int 
   if (it == p->maps.end()) {
     if (p->maps.size() > 256) p->maps.clear();
     CUtensorMap m;
+    KWS_TRY(tc_encode_map(base, planes, H, W, g, &m));
+    it = p->maps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return KWS_OK;
+}
+
+static int tc_encode_map(const void* base, int64_t planes, int H, int W, const TcGeom& g, CUtensorMap* out) {
+  {
+    {
+    CUtensorMap& m = *out;
     // dims: 8 channels, W, rows (of one phase), phases, planes.  Plain tiling is the 1-phase case.
     const cuuint64_t row_stride = (cuuint64_t)W * 16, plane_stride = (cuuint64_t)g.Hpad * W * 16;
     cuuint64_t dims[5], strides[4];
@@ -1018,10 +1037,132 @@ static int tc_get_map(TcResNet* p, const void* base, int64_t planes, int H, int 
                 (long long)planes, g.Wp, g.rows_box, g.phase);
       return KWS_ERR_CUDA;
     }
-    it = p->maps.emplace(key, m).first;
+    }
   }
-  *out = &it->second;
   return KWS_OK;
+}
+
+// ---- whole-network persistent kernel: geometry, shared-memory plan, device tables ----------------
+struct TcFusedPlan {
+  bool ok = false;
+  int Hpad = 0, n_slots = 0, smem_total = 0;
+  int w_off[2] = {0, 0}, ring_off = 0, slot_bytes = 0;
+  std::vector<TcGeom> geoms;
+};
+
+static TcFusedPlan tc_fused_plan(const TcResNet* p, int H, int W) {
+  TcFusedPlan f;
+  const kws_resnet_config& c = p->cfg;
+  if (!p->fused_enabled || c.n_layers < 1 || c.n_layers > kFusedMaxLayers || c.n_labels > 4096) return f;
+  f.Hpad = tc_hpad(c, H);
+  f.n_slots = p->n_sms;
+  const int w_bytes = 9 * p->NKC * 2 * p->CP * 16;
+  f.w_off[0] = 5120;   // control block: barriers, pooled sums, constants, layer descriptors, conv_0 weights
+  f.w_off[1] = f.w_off[0] + round_up(w_bytes, 128);
+  f.ring_off = round_up(f.w_off[1] + w_bytes, 1024);
+  for (int i = 1; i <= c.n_layers; ++i) {
+    TcGeom g;
+    const int d = c.use_dilation ? (1 << ((i - 1) / 3)) : 1;
+    if (!tc_geom(p->NKC, H, f.Hpad, W, d, &g)) return f;
+    f.slot_bytes = std::max(f.slot_bytes, round_up(g.stage_bytes, 128));
+    f.geoms.push_back(g);
+  }
+  f.smem_total = f.ring_off + kFusedStages * f.slot_bytes + 4096;
+  f.ok = f.smem_total <= 227 * 1024;
+  return f;
+}
+
+static size_t tc_fused_ws_bytes(const TcResNet* p, const TcFusedPlan& f, int W, size_t* buf_out) {
+  const size_t buf = round_up<size_t>((size_t)f.n_slots * p->NP * f.Hpad * W * 16, 1024);
+  if (buf_out) *buf_out = buf;
+  return 2 * buf;
+}
+
+template <int NKC>
+static int tc_launch_fused(const TcFusedParams& prm, int grid, int smem, cudaStream_t st) {
+  KWS_CUDA(cudaFuncSetAttribute(resnet_tc_fused_kernel<NKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  resnet_tc_fused_kernel<NKC><<<grid, kTcThreads, smem, st>>>(prm);
+  KWS_CHECK_LAUNCH();
+  return KWS_OK;
+}
+
+static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat, int64_t B, int T, int F, int H, int W,
+                            float* logits, void* ws, cudaStream_t st) {
+  const kws_resnet_config& c = p->cfg;
+  size_t buf = 0;
+  tc_fused_ws_bytes(p, f, W, &buf);
+  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws));
+  __nv_bfloat16* Q = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + buf);
+  const auto key = std::make_tuple(T, F, (const void*)ws);
+  if (p->fused_key != key) {
+    // (re)build the device tables: layer descriptors + one input tensor map per layer
+    const int n = c.n_layers;
+    const size_t maps_off = round_up<size_t>(sizeof(TcLayerDesc) * n, 64);
+    const size_t total = maps_off + sizeof(CUtensorMap) * n;
+    std::vector<unsigned char> host(total, 0);
+    for (int i = 1; i <= n; ++i) {
+      TcLayerDesc L{};
+      L.g = f.geoms[i - 1];
+      L.wpack = p->wpack[i - 1];
+      L.kconst = p->shift_p[i - 1];
+      L.has_skip = (i % 2 == 0) ? 1 : 0;
+      L.in_buf = L.has_skip ? 1 : 0;
+      L.last = (i == n) ? 1 : 0;
+      memcpy(host.data() + sizeof(TcLayerDesc) * (i - 1), &L, sizeof(L));
+      CUtensorMap m;
+      KWS_TRY(tc_encode_map(L.in_buf ? Q : P, (int64_t)f.n_slots * p->NP, H, W, L.g, &m));
+      memcpy(host.data() + maps_off + sizeof(CUtensorMap) * (i - 1), &m, sizeof(m));
+    }
+    if (p->fused_dev) { KWS_CUDA(cudaStreamSynchronize(st)); KWS_CUDA(cudaFree(p->fused_dev)); p->fused_dev = nullptr; }
+    KWS_CUDA(cudaMalloc(&p->fused_dev, total));
+    KWS_CUDA(cudaMemcpyAsync(p->fused_dev, host.data(), total, cudaMemcpyHostToDevice, st));
+    KWS_CUDA(cudaStreamSynchronize(st));   // `host` goes out of scope; this happens once per shape
+    TcFusedParams& q = p->fused_prm;
+    q = TcFusedParams{};
+    q.layers = reinterpret_cast<const TcLayerDesc*>(p->fused_dev);
+    q.maps = reinterpret_cast<const CUtensorMap*>(static_cast<char*>(p->fused_dev) + maps_off);
+    q.conv0_w = p->conv0_w;
+    q.last_scale = p->scale_p[n - 1];
+    q.out_w = p->out_w;
+    q.out_b = p->out_b;
+    q.P = P; q.Q = Q;
+    q.n_layers = n; q.C = c.n_maps; q.n_labels = c.n_labels; q.T = T; q.F = F;
+    q.ph = c.pool_h > 0 ? c.pool_h : 1; q.pw = c.pool_w > 0 ? c.pool_w : 1;
+    q.H = H; q.W = W; q.Hpad = f.Hpad;
+    q.smem_w_off[0] = f.w_off[0]; q.smem_w_off[1] = f.w_off[1];
+    q.smem_ring_off = f.ring_off; q.ring_slot_bytes = f.slot_bytes;
+    p->fused_smem = f.smem_total;
+    p->fused_key = key;
+  }
+  if (f.Hpad > H) {
+    for (__nv_bfloat16* bp : {P, Q}) {
+      zero_pad_rows_kernel<<<256, 256, 0, st>>>(reinterpret_cast<uint4*>(bp), (int64_t)f.n_slots * p->NP, H, f.Hpad, W);
+      KWS_CHECK_LAUNCH();
+    }
+  }
+  TcFusedParams prm = p->fused_prm;
+  prm.feat = feat;
+  prm.logits = logits;
+  prm.B = B;
+  const int grid = (int)std::min<int64_t>(f.n_slots, B);
+  switch (p->NKC) {
+    case 1: return tc_launch_fused<1>(prm, grid, p->fused_smem, st);
+    case 2: return tc_launch_fused<2>(prm, grid, p->fused_smem, st);
+    case 3: return tc_launch_fused<3>(prm, grid, p->fused_smem, st);
+    default: return tc_launch_fused<4>(prm, grid, p->fused_smem, st);
+  }
+}
+
+size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int chunk) {
+  if (!p || !p->supported) return 0;
+  int H, W;
+  tc_map_hw(p->cfg, T, F, &H, &W);
+  if (H < 1 || W < 1 || W > 256 || !tc_layers_ok(p, H, W)) return 0;
+  const int64_t c = tc_chunk(p, B, H, W, chunk);
+  const size_t layered = p->lanes * tc_lane_bytes(p, c, H, W, nullptr);
+  const TcFusedPlan f = tc_fused_plan(p, H, W);
+  // the layer-per-launch path stays available (profiling, shapes the fused kernel cannot stage)
+  return f.ok ? std::max(layered, tc_fused_ws_bytes(p, f, W, nullptr)) : layered;
 }
 
 template <int NKC, bool HAS_PREV, bool DO_POOL>
@@ -1072,6 +1213,11 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
   if (ws == nullptr || ws_bytes < need) {
     set_error("ResNet bf16 forward needs %zu bytes of workspace, got %zu", need, ws_bytes);
     return KWS_ERR_WORKSPACE;
+  }
+  {
+    // whole-network persistent kernel unless per-launch profiling was requested
+    const TcFusedPlan f = tc_fused_plan(p, H, W);
+    if (f.ok && !(prof && prof->enabled)) return tc_fused_forward(p, f, feat, B, T, F, H, W, logits, ws, st);
   }
   const int64_t chunk = tc_chunk(p, B, H, W, chunk_cfg);
   const int Hpad = tc_hpad(c, H);
