@@ -32,9 +32,11 @@
 
 namespace kws {
 
-constexpr int kTcEpiWarps = 8;
 constexpr int kTcIssuers = 3;      // MMA-issuing warps (M-tiles dealt round-robin)
-constexpr int kTcThreads = 32 * (1 + kTcIssuers + kTcEpiWarps);   // warp 0 TMA, warps 1-3 MMA, 8 epilogue warps
+// warp 0 TMA, warps 1-3 MMA, then 4*NKC epilogue warps: warp e owns TMEM lane quarter (warp % 4) and the
+// 16-channel group e / 4 (two planar-8 planes) of EVERY M-tile
+__host__ __device__ constexpr int tc_epi_warps(int NKC) { return 4 * NKC; }
+__host__ __device__ constexpr int tc_threads(int NKC) { return 32 * (1 + kTcIssuers + tc_epi_warps(NKC)); }
 constexpr int kTcMaxMt = 8;       // upper bound of M-tiles per tile (min(8, kAccCols / CP) at run time)
 constexpr int kAccCols = 256;     // TMEM columns per accumulator buffer
 constexpr int kTcMaxLanes = 4;
@@ -207,7 +209,7 @@ struct TcConvParams {
 // HAS_PREV: even layer (adds and rewrites the skip tensor).  DO_POOL: last layer (accumulates the
 // global mean instead of storing the activation).
 template <int NKC, bool HAS_PREV, bool DO_POOL>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(tc_threads(NKC), 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p) {
   constexpr int CP = 16 * NKC;       // padded channels = UMMA N
   constexpr int NP = 2 * NKC;        // 8-channel planes
@@ -237,7 +239,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
   // ---- one-time setup
   if (threadIdx.x == 0) {
     for (int s = 0; s < g.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kTcIssuers); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), kTcIssuers); mbar_init(tempty_bar(a), kTcEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), kTcIssuers); mbar_init(tempty_bar(a), tc_epi_warps(NKC)); }
     mbar_init(wfull_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmap);
@@ -246,7 +248,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
     bulk_load(smem_u32(s_w), p.wpack, W_BYTES, wfull_bar);
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  for (int i = threadIdx.x; i < CP; i += kTcThreads) s_kconst[i] = p.kconst[i];
+  for (int i = threadIdx.x; i < CP; i += tc_threads(NKC)) s_kconst[i] = p.kconst[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -366,39 +368,36 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ================================ epilogue (8 warps) ================================
-    // TMEM lane quarter q = warp % 4 is fixed by hardware; the two warps that share a quarter
-    // take alternate M-tiles.  z = ReLU(acc) (+ skip) - mean, per channel; the per-channel
-    // constants live in registers (pooling variant: shared memory, it needs the registers for sums).
-    const int ew = warp - (1 + kTcIssuers);
+    // ================================ epilogue (4*NKC warps) ================================
+    // Warp e reads TMEM lane quarter q = warp % 4 (fixed by hardware) and the 16 accumulator columns of
+    // channel group j = e / 4, for every M-tile of the tile: z = ReLU(acc) (+ skip) + kconst, two 16-byte
+    // planar-8 stores per position.  The 16 per-channel constants live in registers.
     const int q = warp & 3;
-    const int par = ew >> 2;
+    const int j = (warp - (1 + kTcIssuers)) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int64_t plane_stride = (int64_t)g.Hpad * g.W;   // in 16-byte (8-channel) units
     const int hstep = g.phase ? g.d : 1;
-    const uint4* skip_in = reinterpret_cast<const uint4*>(p.skip);
-    uint4* y_out = reinterpret_cast<uint4*>(p.y);
-    float kc_reg[DO_POOL ? 1 : CP];
-    if constexpr (!DO_POOL) {
+    const uint4* skip_in = reinterpret_cast<const uint4*>(p.skip) + (int64_t)(2 * j) * plane_stride;
+    uint4* y_out = reinterpret_cast<uint4*>(p.y) + (int64_t)(2 * j) * plane_stride;
+    float kc_reg[16];
 #pragma unroll
-      for (int c = 0; c < CP; ++c) kc_reg[c] = s_kconst[c];
-    }
-    float psum[DO_POOL ? CP : 1];   // this thread's share of sum_{h,w} z of the current utterance (resnet.py:57-58)
+    for (int c = 0; c < 16; ++c) kc_reg[c] = s_kconst[16 * j + c];
+    float psum[DO_POOL ? 16 : 1];   // this thread's share of sum_{h,w} z of the current utterance (resnet.py:57-58)
     int pool_b = -1;
     auto pool_flush = [&]() {
       if constexpr (DO_POOL) {
         if (pool_b >= 0) {   // warp-reduce the 32 positions, one atomic per channel
 #pragma unroll
-          for (int c = 0; c < CP; ++c) {
+          for (int c = 0; c < 16; ++c) {
             float sum = psum[c];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == (c & 31)) atomicAdd(p.pool_sum + (int64_t)pool_b * CP + c, sum);
+            if (lane == c) atomicAdd(p.pool_sum + (int64_t)pool_b * CP + 16 * j + c, sum);
           }
         }
 #pragma unroll
-        for (int c = 0; c < CP; ++c) psum[c] = 0.f;
+        for (int c = 0; c < 16; ++c) psum[c] = 0.f;
       }
     };
     pool_flush();
@@ -410,7 +409,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       if (rows <= 0) continue;
       const int n_mt = (rows * g.Wp + 127) >> 7;
       const int64_t utt_base = ((int64_t)b * NP) * plane_stride + (int64_t)(r0 * hstep + ph) * g.W;
-      // position of this thread in M-tile `mt`: valid flag and offset (16-byte units) inside plane 0
+      // position of this thread in M-tile `mt`: valid flag and offset (16-byte units) inside a plane
       auto locate = [&](int mt, bool& valid) -> int64_t {
         const int pos = mt * 128 + q * 32 + lane;
         const int r = pos / g.Wp;
@@ -420,44 +419,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
       };
       // The skip tensor is fetched one M-tile ahead; the first fetch is issued BEFORE waiting for
       // the accumulators, so its latency hides behind the MMAs of this tile.
-      uint4 pv_next[HAS_PREV ? NP : 1];
+      uint4 pv_next[2];
       if constexpr (HAS_PREV) {
         bool v0;
-        const int64_t b0 = locate(par, v0);
-        if (v0) {
-#pragma unroll
-          for (int pl = 0; pl < NP; ++pl) pv_next[pl] = skip_in[b0 + pl * plane_stride];
-        }
+        const int64_t b0 = locate(0, v0);
+        if (v0) { pv_next[0] = skip_in[b0]; pv_next[1] = skip_in[b0 + plane_stride]; }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      for (int mt = par; mt < n_mt; mt += 2) {
+      for (int mt = 0; mt < n_mt; ++mt) {
         bool valid;
         const int64_t base = locate(mt, valid);
-        uint4 pv[HAS_PREV ? NP : 1];
+        uint4 pv[2];
         if constexpr (HAS_PREV) {
-#pragma unroll
-          for (int pl = 0; pl < NP; ++pl) pv[pl] = pv_next[pl];
+          pv[0] = pv_next[0]; pv[1] = pv_next[1];
           bool v2;
-          const int64_t b2 = locate(mt + 2, v2);
-          if (v2) {
-#pragma unroll
-            for (int pl = 0; pl < NP; ++pl) pv_next[pl] = skip_in[b2 + pl * plane_stride];
-          }
+          const int64_t b2 = locate(mt + 1, v2);
+          if (v2) { pv_next[0] = skip_in[b2]; pv_next[1] = skip_in[b2 + plane_stride]; }
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP;
-        uint32_t v[NKC][16];
-#pragma unroll
-        for (int j = 0; j < NKC; ++j) tmem_ld16(taddr + 16 * j, v[j]);
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP + 16 * j, v);
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
-          for (int pl = 0; pl < NP; ++pl) {
+          for (int hf = 0; hf < 2; ++hf) {
             float x[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[pl >> 1][8 * (pl & 1) + e]), 0.f);
+            for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[8 * hf + e]), 0.f) + kc_reg[8 * hf + e];
             if constexpr (HAS_PREV) {
-              const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[pl]);
+              const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[hf]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 f = __bfloat1622float2(pb[e]);
@@ -467,14 +457,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
             }
             if constexpr (DO_POOL) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) psum[8 * pl + e] += x[e] + s_kconst[8 * pl + e];
+              for (int e = 0; e < 8; ++e) psum[8 * hf + e] += x[e];
             } else {
               uint4 yo;
               __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                yb[e] = __floats2bfloat162_rn(x[2 * e] + kc_reg[8 * pl + 2 * e], x[2 * e + 1] + kc_reg[8 * pl + 2 * e + 1]);
-              y_out[base + pl * plane_stride] = yo;
+              for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+              y_out[base + hf * plane_stride] = yo;
             }
           }
         }
@@ -1081,7 +1070,7 @@ static size_t tc_fused_ws_bytes(const TcResNet* p, const TcFusedPlan& f, int W, 
 template <int NKC>
 static int tc_launch_fused(const TcFusedParams& prm, int grid, int smem, cudaStream_t st) {
   KWS_CUDA(cudaFuncSetAttribute(resnet_tc_fused_kernel<NKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  resnet_tc_fused_kernel<NKC><<<grid, kTcThreads, smem, st>>>(prm);
+  resnet_tc_fused_kernel<NKC><<<grid, tc_threads(NKC), smem, st>>>(prm);
   KWS_CHECK_LAUNCH();
   return KWS_OK;
 }
@@ -1172,7 +1161,7 @@ static int tc_launch_conv3(const CUtensorMap& map, const TcConvParams& prm, int 
   static const bool use_pdl = [] { const char* e = std::getenv("HONK2_TC_PDL"); return e == nullptr || std::atoi(e) != 0; }();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kTcThreads);
+  cfg.blockDim = dim3(tc_threads(NKC));
   cfg.dynamicSmemBytes = prm.g.smem_total;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -50,8 +50,10 @@ struct TcFusedParams {
 };
 
 template <int NKC>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(tc_threads(NKC), 1)
 resnet_tc_fused_kernel(const TcFusedParams p) {
+  constexpr int kThreads = tc_threads(NKC);
+  constexpr int kEpiWarps = tc_epi_warps(NKC);
   constexpr int CP = 16 * NKC;
   constexpr int NP = 2 * NKC;
   constexpr int W_HALF = CP * 16;
@@ -84,7 +86,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
   // ---- one-time setup
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFusedStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kTcIssuers); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), kTcIssuers); mbar_init(tempty_bar(a), kTcEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), kTcIssuers); mbar_init(tempty_bar(a), kEpiWarps); }
     mbar_init(wfull_bar(0), 1);
     mbar_init(wfull_bar(1), 1);
     fence_barrier_init();
@@ -95,11 +97,11 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
     }
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  for (int i = threadIdx.x; i < CP * 12; i += kTcThreads) {
+  for (int i = threadIdx.x; i < CP * 12; i += kThreads) {
     const int c = i / 12, k = i - c * 12;
     s_w0[i] = (k < 9 && c < p.C) ? p.conv0_w[c * 9 + k] : 0.f;
   }
-  for (int i = threadIdx.x; i < CP; i += kTcThreads) {
+  for (int i = threadIdx.x; i < CP; i += kThreads) {
     s_pool[i] = 0.f;
     if (n_seq > 0) s_kconst[i] = p.layers[0].kconst[i];
   }
@@ -133,10 +135,10 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     // =============================== conv_0 -> P (epilogue warps) ===============================
     if (warp > kTcIssuers) {
-      const int et = threadIdx.x - 32 * (1 + kTcIssuers);           // 0 .. 255
+      const int et = threadIdx.x - 32 * (1 + kTcIssuers);           // 0 .. 32 * kEpiWarps - 1
       const float* src = p.feat + b * (int64_t)p.T * p.F;
       const float inv = 1.f / (float)(p.ph * p.pw);
-      for (int pix = et; pix < p.H * p.W; pix += 32 * kTcEpiWarps) {
+      for (int pix = et; pix < p.H * p.W; pix += 32 * kEpiWarps) {
         const int ho = pix / p.W, wo = pix - ho * p.W;
         for (int pl = 0; pl < NP; ++pl) {
           float a8[8];
@@ -276,15 +278,20 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
           if (acc == 0) acc_phase ^= 1;
         }
       } else {
-        // ================================ epilogue (8 warps) ================================
-        const int ew = warp - (1 + kTcIssuers);
+        // ================================ epilogue (4*NKC warps) ================================
+        // warp e: TMEM lane quarter q = warp % 4, channel group j = e / 4 (16 channels = planes 2j, 2j+1)
         const int q = warp & 3;
-        const int par = ew >> 2;
+        const int j = (warp - (1 + kTcIssuers)) >> 2;
         const int hstep = g.phase ? g.d : 1;
         const bool has_skip = L.has_skip != 0, last = L.last != 0;
-        const uint4* skip_in = bufP;                                     // even layers read AND write P
-        uint4* y_out = has_skip ? bufP : bufQ;
-        const float* kcst = s_kconst + cur * CP;
+        const uint4* skip_in = bufP + (int64_t)(2 * j) * plane_stride;          // even layers read AND write P
+        uint4* y_out = (has_skip ? bufP : bufQ) + (int64_t)(2 * j) * plane_stride;
+        float kc_reg[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) kc_reg[c] = s_kconst[cur * CP + 16 * j + c];
+        float psum[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) psum[c] = 0.f;
         for (int tix = 0; tix < n_tiles; ++tix) {
           int ph, r0, rows;
           tile_decode(g, tix, ph, r0, rows);
@@ -298,69 +305,52 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
             valid = (w >= 0) && (r < rows) && (mt < n_mt);
             return tile_base + (int64_t)(r * hstep) * g.W + w;
           };
-          uint4 pv_next[NP];
+          uint4 pv_next[2];
           if (has_skip) {
             bool v0;
-            const int64_t b0 = locate(par, v0);
-            if (v0) {
-#pragma unroll
-              for (int pl = 0; pl < NP; ++pl) pv_next[pl] = skip_in[b0 + pl * plane_stride];
-            }
+            const int64_t b0 = locate(0, v0);
+            if (v0) { pv_next[0] = skip_in[b0]; pv_next[1] = skip_in[b0 + plane_stride]; }
           }
           mbar_wait(tfull_bar(acc), acc_phase);
           tc_fence_after();
-          for (int mt = par; mt < n_mt; mt += 2) {
+          for (int mt = 0; mt < n_mt; ++mt) {
             bool valid;
             const int64_t base = locate(mt, valid);
-            uint4 pv[NP];
+            uint4 pv[2];
             if (has_skip) {
-#pragma unroll
-              for (int pl = 0; pl < NP; ++pl) pv[pl] = pv_next[pl];
+              pv[0] = pv_next[0]; pv[1] = pv_next[1];
               bool v2;
-              const int64_t b2 = locate(mt + 2, v2);
-              if (v2) {
-#pragma unroll
-                for (int pl = 0; pl < NP; ++pl) pv_next[pl] = skip_in[b2 + pl * plane_stride];
-              }
+              const int64_t b2 = locate(mt + 1, v2);
+              if (v2) { pv_next[0] = skip_in[b2]; pv_next[1] = skip_in[b2 + plane_stride]; }
             }
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP;
-            uint32_t v[NKC][16];
-#pragma unroll
-            for (int j = 0; j < NKC; ++j) tmem_ld16(taddr + 16 * j, v[j]);
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP + 16 * j, v);
             tmem_ld_wait();
+            if (valid) {
 #pragma unroll
-            for (int pl = 0; pl < NP; ++pl) {
-              float x[8];
+              for (int hf = 0; hf < 2; ++hf) {
+                float x[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[pl >> 1][8 * (pl & 1) + e]), 0.f);
-              if (has_skip) {
-                const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[pl]);
+                for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[8 * hf + e]), 0.f) + kc_reg[8 * hf + e];
+                if (has_skip) {
+                  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[hf]);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(pb[e]);
-                  x[2 * e] += f.x;
-                  x[2 * e + 1] += f.y;
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(pb[e]);
+                    x[2 * e] += f.x;
+                    x[2 * e + 1] += f.y;
+                  }
                 }
-              }
-              const float4 k0 = *reinterpret_cast<const float4*>(kcst + 8 * pl);
-              const float4 k1 = *reinterpret_cast<const float4*>(kcst + 8 * pl + 4);
-              x[0] += k0.x; x[1] += k0.y; x[2] += k0.z; x[3] += k0.w;
-              x[4] += k1.x; x[5] += k1.y; x[6] += k1.z; x[7] += k1.w;
-              if (last) {
-                // fused global mean (resnet.py:57-58): warp-reduce the 32 positions, one shared atomic per channel
+                if (last) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  float sum = valid ? x[e] : 0.f;
+                  for (int e = 0; e < 8; ++e) psum[8 * hf + e] += x[e];
+                } else {
+                  uint4 yo;
+                  __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
 #pragma unroll
-                  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                  if (lane == e) atomicAdd(s_pool + 8 * pl + e, sum);
+                  for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+                  y_out[base + hf * plane_stride] = yo;
                 }
-              } else if (valid) {
-                uint4 yo;
-                __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-                y_out[base + pl * plane_stride] = yo;
               }
             }
           }
@@ -369,6 +359,16 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
           if (lane == 0) mbar_arrive(tempty_bar(acc));
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
+        }
+        if (last) {
+          // fused global mean (resnet.py:57-58): warp-reduce the 32 positions, one shared atomic per channel
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float sum = psum[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == c) atomicAdd(s_pool + 16 * j + c, sum);
+          }
         }
         __threadfence();
         fence_async_all();   // this layer's activations -> visible to the next layer's TMA loads
@@ -380,7 +380,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
 
     // =============================== logits (resnet.py:59) ===============================
     if (n_layers > 0) {
-      for (int lb = threadIdx.x; lb < p.n_labels; lb += kTcThreads) {
+      for (int lb = threadIdx.x; lb < p.n_labels; lb += kThreads) {
         const float inv = 1.f / (float)(p.H * p.W);
         float v = __ldg(p.out_b + lb);
         // s_pool holds sums of z = x - mean; the BatchNorm output mean is z_mean / sigma (resnet.py:55-58)
@@ -389,7 +389,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
         p.logits[b * p.n_labels + lb] = v;
       }
       __syncthreads();
-      for (int i = threadIdx.x; i < CP; i += kTcThreads) s_pool[i] = 0.f;
+      for (int i = threadIdx.x; i < CP; i += kThreads) s_pool[i] = 0.f;
       // the next writer of s_pool is many barriers away (last layer of the next utterance)
     }
   }
