@@ -47,6 +47,7 @@ struct TcFusedParams {
   int64_t B;
   int n_layers, C, n_labels, T, F, ph, pw, H, W, Hpad;
   int smem_w_off[2], smem_ring_off, ring_slot_bytes;
+  int l2_policy;   // 1: buffer P (read twice, rewritten in place) evict_last, buffer Q (write once, read once) evict_first
 };
 
 template <int NKC>
@@ -115,6 +116,13 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
   uint4* bufP = reinterpret_cast<uint4*>(p.P) + slot_base;
   uint4* bufQ = reinterpret_cast<uint4*>(p.Q) + slot_base;
 
+  // The two slot buffers of all CTAs together are about as large as the L2, so plain LRU thrashes.  P is
+  // kept (evict_last): it is read as the odd layers' input, read again as the skip tensor and rewritten in
+  // place.  Q streams (evict_first): written once, read once.
+  const bool use_pol = p.l2_policy != 0;
+  const uint64_t pol_keep = l2_policy_evict_last();
+  const uint64_t pol_stream = l2_policy_evict_first();
+
   // pipeline state (persists across layers and utterances; every role walks the same tile sequence)
   int stage = 0, acc = 0;
   uint32_t phase = 0, acc_phase = 0;
@@ -137,6 +145,50 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
     if (warp > kTcIssuers) {
       const int et = threadIdx.x - 32 * (1 + kTcIssuers);           // 0 .. 32 * kEpiWarps - 1
       const float* src = p.feat + b * (int64_t)p.T * p.F;
+      if (p.ph == 1 && p.pw == 1) {
+        // no pooling (res15): 4 consecutive pixels x all channels per item, every weight read feeds 4 FMAs
+        const int groups = (p.W + 3) >> 2;
+        for (int item = et; item < p.H * groups; item += 32 * kEpiWarps) {
+          const int h = item / groups, w0 = (item - h * groups) * 4;
+          float pch[3][6];
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int e = 0; e < 6; ++e) {
+              const int hh = h + a - 1, ww = w0 + e - 1;
+              pch[a][e] = (hh >= 0 && hh < p.T && ww >= 0 && ww < p.F) ? __ldg(src + (int64_t)hh * p.F + ww) : 0.f;
+            }
+          for (int pl = 0; pl < NP; ++pl) {
+            float a4[4][8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float* wc9 = s_w0 + (pl * 8 + e) * 12;
+              const float4 wa = *reinterpret_cast<const float4*>(wc9);
+              const float4 wb = *reinterpret_cast<const float4*>(wc9 + 4);
+              const float w8 = wc9[8];
+#pragma unroll
+              for (int px = 0; px < 4; ++px) {
+                float v = pch[0][px] * wa.x;
+                v = fmaf(pch[0][px + 1], wa.y, v); v = fmaf(pch[0][px + 2], wa.z, v);
+                v = fmaf(pch[1][px], wa.w, v); v = fmaf(pch[1][px + 1], wb.x, v); v = fmaf(pch[1][px + 2], wb.y, v);
+                v = fmaf(pch[2][px], wb.z, v); v = fmaf(pch[2][px + 1], wb.w, v); v = fmaf(pch[2][px + 2], w8, v);
+                a4[px][e] = fmaxf(v, 0.f);
+              }
+            }
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+              if (w0 + px < p.W) {
+                uint4 o;
+                __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(a4[px][2 * e], a4[px][2 * e + 1]);
+                uint4* dst = bufP + pl * plane_stride + (int64_t)h * p.W + w0 + px;
+                if (use_pol) st_hint(dst, o, pol_keep); else *dst = o;
+              }
+            }
+          }
+        }
+      } else {
       const float inv = 1.f / (float)(p.ph * p.pw);
       for (int pix = et; pix < p.H * p.W; pix += 32 * kEpiWarps) {
         const int ho = pix / p.W, wo = pix - ho * p.W;
@@ -173,6 +225,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
           for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(a8[2 * e] * inv, a8[2 * e + 1] * inv);
           bufP[pl * plane_stride + pix] = o;
         }
+      }
       }
       __threadfence();
       fence_async_all();   // generic-proxy global writes -> visible to the TMA (async proxy) reads of layer 1
@@ -213,8 +266,13 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
               const uint32_t sbase = smem_u32(s_ring + (size_t)stage * p.ring_slot_bytes);
               for (int half = 0; half < 2; ++half)
                 for (int bx = 0; bx < g.n_boxes; ++bx)
-                  tma_load_5d(sbase + half * g.slab_bytes + bx * g.box_stride, map, full_bar(stage), 0, -g.dpad,
-                              r0 + g.h_start[bx], ph, (int)blockIdx.x * NP + 2 * kc + half);
+                  if (use_pol)
+                    tma_load_5d_hint(sbase + half * g.slab_bytes + bx * g.box_stride, map, full_bar(stage), 0, -g.dpad,
+                                     r0 + g.h_start[bx], ph, (int)blockIdx.x * NP + 2 * kc + half,
+                                     L.in_buf ? pol_stream : pol_keep);
+                  else
+                    tma_load_5d(sbase + half * g.slab_bytes + bx * g.box_stride, map, full_bar(stage), 0, -g.dpad,
+                                r0 + g.h_start[bx], ph, (int)blockIdx.x * NP + 2 * kc + half);
               if (++stage == kFusedStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -309,7 +367,10 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
           if (has_skip) {
             bool v0;
             const int64_t b0 = locate(0, v0);
-            if (v0) { pv_next[0] = skip_in[b0]; pv_next[1] = skip_in[b0 + plane_stride]; }
+            if (v0) {
+              pv_next[0] = use_pol ? ld_hint(skip_in + b0, pol_keep) : skip_in[b0];
+              pv_next[1] = use_pol ? ld_hint(skip_in + b0 + plane_stride, pol_keep) : skip_in[b0 + plane_stride];
+            }
           }
           mbar_wait(tfull_bar(acc), acc_phase);
           tc_fence_after();
@@ -321,7 +382,10 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
               pv[0] = pv_next[0]; pv[1] = pv_next[1];
               bool v2;
               const int64_t b2 = locate(mt + 1, v2);
-              if (v2) { pv_next[0] = skip_in[b2]; pv_next[1] = skip_in[b2 + plane_stride]; }
+              if (v2) {
+                pv_next[0] = use_pol ? ld_hint(skip_in + b2, pol_keep) : skip_in[b2];
+                pv_next[1] = use_pol ? ld_hint(skip_in + b2 + plane_stride, pol_keep) : skip_in[b2 + plane_stride];
+              }
             }
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP + 16 * j, v);
@@ -349,7 +413,8 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
                   __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-                  y_out[base + hf * plane_stride] = yo;
+                  if (use_pol) st_hint(y_out + base + hf * plane_stride, yo, has_skip ? pol_keep : pol_stream);
+                  else y_out[base + hf * plane_stride] = yo;
                 }
               }
             }
