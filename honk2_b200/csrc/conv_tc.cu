@@ -799,7 +799,13 @@ struct TcResNet {
   cudaEvent_t ev_start = nullptr, ev_done[kTcMaxLanes] = {};
 };
 
-static int tc_max_mt(int CP) { return std::min(kTcMaxMt, kAccCols / CP); }
+static int tc_max_mt(int CP) {
+  // M-tiles per tile, bounded by the TMEM accumulator buffer (HONK2_TC_MAXMT lowers it, for experiments:
+  // measured on B200, larger tiles win even though 5 M-tiles do not divide evenly over 3 issuer warps)
+  static const int env = [] { const char* e = std::getenv("HONK2_TC_MAXMT"); return e ? std::atoi(e) : 0; }();
+  const int cap = std::min(kTcMaxMt, kAccCols / CP);
+  return env > 0 ? std::max(1, std::min(cap, env)) : cap;
+}
 
 // Phase tiling pays when the dilation is large: a tile of R consecutive rows needs R + 2d (or 3R) input
 // rows, a tile of R rows spaced d apart needs R + 2.
@@ -1105,7 +1111,7 @@ static int tc_launch_fused(const TcFusedParams& prm, int grid, int smem, cudaStr
 }
 
 static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat, int64_t B, int T, int F, int H, int W,
-                            float* logits, void* ws, cudaStream_t st) {
+                            float* logits, void* ws, LaunchProfiler* prof, cudaStream_t st) {
   const kws_resnet_config& c = p->cfg;
   size_t buf = 0;
   tc_fused_ws_bytes(p, f, W, &buf);
@@ -1156,12 +1162,14 @@ static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat
     p->fused_smem = f.smem_total;
     p->fused_key = key;
   }
+  if (prof) prof->tick(1, st);
   if (f.Hpad > H) {
     for (__nv_bfloat16* bp : {P, Q}) {
       zero_pad_rows_kernel<<<256, 256, 0, st>>>(reinterpret_cast<uint4*>(bp), (int64_t)f.n_slots * p->NP, H, f.Hpad, W);
       KWS_CHECK_LAUNCH();
     }
   }
+  if (prof) prof->tick(0, st);   // the whole network is one launch: it IS the dominant kernel
   TcFusedParams prm = p->fused_prm;
   prm.feat = feat;
   prm.logits = logits;
@@ -1239,7 +1247,10 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
   {
     // whole-network persistent kernel unless per-launch profiling was requested
     const TcFusedPlan f = tc_fused_plan(p, H, W);
-    if (f.ok && !(prof && prof->enabled)) return tc_fused_forward(p, f, feat, B, T, F, H, W, logits, ws, st);
+    static const bool prof_layered = [] { const char* e = std::getenv("HONK2_TC_PROFILE_LAYERED"); return e && std::atoi(e) != 0; }();
+    if (f.ok && !(prof && prof->enabled && prof_layered)) {
+      return tc_fused_forward(p, f, feat, B, T, F, H, W, logits, ws, prof, st);
+    }
   }
   const int64_t chunk = tc_chunk(p, B, H, W, chunk_cfg);
   const int Hpad = tc_hpad(c, H);

@@ -59,6 +59,9 @@ def profile_layers(model, audio_processor, wave_sets, steps):
     finally:
         lib.kws_model_set_profile(st["handle"], 0)
     launches = int(conv_n.value)
+    if launches == steps and kernel.startswith("conv3x3"):
+        kernel = ("resnet_tc_fused_kernel: conv_0 + %d x (conv3x3 + ReLU + skip + BN) + mean + Linear in ONE launch "
+                  "(FLOPs counted: the C->C convolutions)" % model.n_layers)
     return {"conv_ms": conv_ms.value, "conv_launches": launches, "other_ms": other_ms.value,
             "other_launches": int(other_n.value), "frontend_ms": fe_ms,
             "total_ms": conv_ms.value + other_ms.value + fe_ms,
