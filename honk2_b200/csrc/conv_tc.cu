@@ -1175,6 +1175,25 @@ static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat
   prm.logits = logits;
   prm.B = B;
   const int grid = (int)std::min<int64_t>(f.n_slots, B);
+  static const bool dbg_on = [] { const char* e = std::getenv("HONK2_TC_DEBUG"); return e && std::atoi(e) != 0; }();
+  static long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
+    prm.debug = dbg_buf;
+  }
+  struct DbgPrint {
+    long long* buf; cudaStream_t st;
+    ~DbgPrint() {
+      if (!buf) return;
+      long long h[16];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+      const double tot = (double)(h[0] + h[1] + h[2] + h[3] + h[4] + h[5]);
+      fprintf(stderr, "[fused dbg] issuer 0 of CTA 0, %lld utterances, cycles: conv_0 wait %.1f%%, layer barrier (drain) %.1f%%, "
+              "accumulator-free wait %.1f%%, TMA-data wait %.1f%%, issuing MMAs %.1f%% (total %.0f, %.0f per utterance)\n",
+              h[6], 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, tot, tot / (double)h[6]);
+    }
+  } dbg_print{dbg_on ? dbg_buf : nullptr, st};
   switch (p->NKC) {
     case 1: return tc_launch_fused<1>(prm, grid, p->fused_smem, st);
     case 2: return tc_launch_fused<2>(prm, grid, p->fused_smem, st);

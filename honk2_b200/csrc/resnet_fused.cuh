@@ -47,6 +47,7 @@ struct TcFusedParams {
   int64_t B;
   int n_layers, C, n_labels, T, F, ph, pw, H, W, Hpad;
   int smem_w_off[2], smem_ring_off, ring_slot_bytes;
+  long long* debug;   // optional [16] cycle counters written by CTA 0's first issuer thread (nullptr = off)
   int l2_policy;   // 1: buffer P (read twice, rewritten in place) evict_last, buffer Q (write once, read once) evict_first
 };
 
@@ -139,6 +140,10 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
     }
   };
 
+  // cycle accounting of one issuer thread (HONK2_TC_DEBUG=1).  BAR.SYNC blocks lazily, so the layer-barrier
+  // wait shows up in the first bucket sampled AFTER the barrier (dbg_bar), not right behind __syncthreads.
+  long long dbg_bar = 0, dbg_tempty = 0, dbg_full = 0, dbg_issue = 0, dbg_conv0 = 0, dbg_t = clock64();
+  const bool dbg = p.debug != nullptr && blockIdx.x == 0 && threadIdx.x == 32;
   int64_t seq = 0;   // running (utterance, layer) counter: weight buffer = seq & 1
   for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
     // =============================== conv_0 -> P (epilogue warps) ===============================
@@ -231,6 +236,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
       fence_async_all();   // generic-proxy global writes -> visible to the TMA (async proxy) reads of layer 1
     }
     __syncthreads();
+    if (dbg) { const long long t = clock64(); dbg_conv0 += t - dbg_t; dbg_t = t; }
 
     for (int l = 0; l < n_layers; ++l, ++seq) {
       const int cur = (int)(seq & 1);
@@ -293,6 +299,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
         const int first_tap = side ? 0 : 1;
         const bool leader = elect_one();
         mbar_wait(wfull_bar(cur), (uint32_t)((seq >> 1) & 1));   // this layer's weights have landed
+        if (dbg) { const long long t = clock64(); dbg_bar += t - dbg_t; dbg_t = t; }
         for (int tix = 0; tix < n_tiles; ++tix) {
           int ph, r0, rows;
           tile_decode(g, tix, ph, r0, rows);
@@ -300,11 +307,13 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
           const int n_mt = (rows * g.Wp + 127) >> 7;
           mbar_wait(tempty_bar(acc), acc_phase ^ 1);
           tc_fence_after();
+          if (dbg) { const long long t = clock64(); dbg_tempty += t - dbg_t; dbg_t = t; }
           const uint32_t d_base = tmem_base + acc * kAccCols + me * CP;
 #pragma unroll
           for (int kc = 0; kc < NKC; ++kc) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
+            if (dbg) { const long long t = clock64(); dbg_full += t - dbg_t; dbg_t = t; }
             if (leader) {
               const uint32_t a_lo_stage =
                   (((smem_u32(s_ring + (size_t)stage * p.ring_slot_bytes) >> 4) + me * 128) & 0x3FFFu) | a_lo_fields;
@@ -330,6 +339,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
               if (kc == NKC - 1) umma_commit(tfull_bar(acc));
             }
             __syncwarp();
+            if (dbg) { const long long t = clock64(); dbg_issue += t - dbg_t; dbg_t = t; }
             if (++stage == kFusedStages) { stage = 0; phase ^= 1; }
           }
           acc ^= 1;
@@ -459,6 +469,10 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
     }
   }
 
+  if (dbg) {
+    p.debug[0] = dbg_conv0; p.debug[1] = dbg_bar; p.debug[2] = dbg_tempty; p.debug[3] = dbg_full;
+    p.debug[4] = dbg_issue; p.debug[5] = 0; p.debug[6] = n_my;
+  }
   // ---- teardown
   tc_fence_before();
   __syncthreads();

@@ -42,15 +42,20 @@ struct Cfg {
   int a_stride;   // bytes added to the A start address per MMA (0 = same tile every time)
   int iters;      // MMAs per issuer
   int a_off;      // constant byte offset of the A start address (16-byte granular misalignment)
+  int b_rot;      // rotate the B operand over this many 1536-byte slabs (0/1 = fixed)
+  int ld_warps;   // extra warps that stream tcgen05.ld from TMEM while the MMAs run (epilogue emulation)
+  int st_warps;   // extra warps that stream st.shared.v4 into a spare smem region (TMA-write emulation)
 };
 
-__global__ void __launch_bounds__(160, 1) umma_bench_kernel(Cfg c, long long* cycles) {
+__global__ void __launch_bounds__(672, 1) umma_bench_kernel(Cfg c, long long* cycles) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bars[8];
   __shared__ uint32_t tmem_slot;
+  __shared__ volatile int s_done;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i % 7;
   if (threadIdx.x == 0) {
+    s_done = 0;
     for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -68,21 +73,53 @@ __global__ void __launch_bounds__(160, 1) umma_bench_kernel(Cfg c, long long* cy
   if (warp >= 1 && warp <= c.issuers && lane == 0) {
     const int me = warp - 1;
     const uint32_t a_base = smem_u32(smem) + 1024;
-    const uint32_t b_base = smem_u32(smem) + 160 * 1024;
+    const uint32_t b_base = smem_u32(smem) + 128 * 1024;
     const int cols_per_issuer = 512 / c.issuers;
+    // tight issue loop: no divisions, descriptors advanced incrementally (the issue cost must stay below the
+    // pipe cost for the measurement to show the pipe)
+    const uint32_t a_lo0 = ((a_base + me * 2048 + c.a_off) >> 4) & 0x3FFF;
+    const uint32_t a_hi_lbo = ((uint32_t)(c.lbo >> 4) & 0x3FFF) << 16;
+    const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFF) | ((((uint32_t)c.N * 16) >> 4) << 16);
+    const uint32_t hi = (c.layout == 0) ? ((128u >> 4) | (1u << 14)) : ((1024u >> 4) | (1u << 14) | (2u << 29));
+    const uint32_t a_step = (uint32_t)c.a_stride >> 4;
+    int ai = 0, bi = 0, di = 0;
+    uint32_t a_lo = a_lo0, b_lo = b_lo0, d = tmem + me * cols_per_issuer;
+    const int b_rot = c.b_rot > 1 ? c.b_rot : 1;
     t0 = clock64();
     for (int i = 0; i < c.iters; ++i) {
-      const uint32_t a_addr = a_base + (uint32_t)((i % 32) * c.a_stride) + me * 2048 + c.a_off;
-      uint64_t ad, bd;
-      if (c.layout == 0) { ad = desc(a_addr, c.lbo, 128, 0); bd = desc(b_base, c.N * 16, 128, 0); }
-      else { ad = desc(a_addr, 16, 1024, 2); bd = desc(b_base, 16, 1024, 2); }
-      const uint32_t d = tmem + me * cols_per_issuer + (i % c.n_acc) * c.N;
+      const uint64_t ad = ((uint64_t)hi << 32) | (a_lo | a_hi_lbo);
+      const uint64_t bd = ((uint64_t)hi << 32) | b_lo;
       umma(d, ad, bd, idesc, i >= c.n_acc ? 1u : 0u);
+      a_lo += a_step; if (++ai == 32) { ai = 0; a_lo = a_lo0; }
+      b_lo += 96; if (++bi == b_rot) { bi = 0; b_lo = b_lo0; }
+      d += c.N; if (++di == c.n_acc) { di = 0; d = tmem + me * cols_per_issuer; }
     }
     umma_commit(smem_u32(&bars[me]));
     mbar_wait(smem_u32(&bars[me]), 0);
     t1 = clock64();
     cycles[blockIdx.x * 4 + me] = t1 - t0;
+    atomicAdd((int*)&s_done, 1);
+  } else if (warp >= 5 && warp < 5 + c.ld_warps) {
+    // epilogue emulation: keep reading 16 TMEM columns of this warp's lane quarter
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 496;
+    uint32_t acc = 0;
+    while (s_done < c.issuers) {
+      uint32_t v[16];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                     "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      acc += v[0] ^ v[15];
+    }
+    if (acc == 0x12345678u) cycles[0] = 1;
+  } else if (warp >= 17 && warp < 17 + c.st_warps) {
+    // TMA-write emulation: stream 16-byte stores into a spare 24 KB region
+    uint4* dst = reinterpret_cast<uint4*>(smem + 172 * 1024);
+    int k = 0;
+    while (s_done < c.issuers) {
+      dst[(k * 32 + lane) % 1536] = make_uint4(k, k, k, k);
+      ++k;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -98,31 +135,23 @@ int main() {
   cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   std::vector<Cfg> cfgs;
   const int IT = 4000;
-  for (int N : {48, 96, 144, 192, 240}) cfgs.push_back({N, 0, 11904, 512 / N > 5 ? 5 : 512 / N, 1, 2048, IT});
-  for (int N : {48, 96, 240}) cfgs.push_back({N, 2, 0, 512 / N > 5 ? 5 : 512 / N, 1, 4096, IT});   // 128B swizzle
-  cfgs.push_back({48, 0, 128, 5, 1, 2048, IT});        // K halves adjacent-ish (different core-matrix order)
-  cfgs.push_back({48, 0, 11904, 1, 1, 2048, IT});      // one accumulator: dependent chain
-  cfgs.push_back({48, 0, 11904, 5, 1, 0, IT});         // same A tile every time
-  cfgs.push_back({48, 0, 11904, 2, 2, 2048, IT});      // 2 issuers
-  cfgs.push_back({48, 0, 11904, 2, 4, 2048, IT});      // 4 issuers
-  cfgs.push_back({48, 0, 11904, 1, 4, 2048, IT});      // 4 issuers, 1 accumulator each
-  cfgs.push_back({96, 0, 11904, 1, 4, 2048, IT});
-  cfgs.push_back({240, 0, 11904, 1, 2, 2048, IT});
-  cfgs.push_back({48, 0, 11904, 2, 4, 2048, IT, 16});     // A start misaligned by 16 B (dw = +-1 at d = 1)
-  cfgs.push_back({48, 0, 11904, 2, 4, 2048, IT, 64});     // misaligned by 64 B (d = 4)
-  cfgs.push_back({48, 0, 11904, 2, 4, 656, IT, 0});       // row pitch 41 positions
-  cfgs.push_back({48, 0, 11904, 2, 4, 2048, IT, 128});    // aligned shift (d = 8)
-  cfgs.push_back({48, 0, 11968, 2, 4, 2048, IT, 0});      // LBO not a multiple of 128
-  cfgs.push_back({48, 0, 12032, 2, 4, 2048, IT, 0});      // LBO = 94 * 128
-  cfgs.push_back({48, 2, 0, 2, 4, 4096, IT, 0});          // 128B swizzle, 4 issuers
-  cfgs.push_back({32, 0, 11904, 2, 4, 2048, IT, 0});
-  cfgs.push_back({64, 0, 11904, 2, 4, 2048, IT, 0});
-  printf("%4s %6s %6s %5s %7s %8s %5s | %12s %14s %10s\n", "N", "layout", "lbo", "n_acc", "issuers", "a_stride", "a_off", "cyc/MMA/iss",
+  //            N  lay lbo    nacc iss a_stride it  a_off b_rot ld st
+  for (int iss : {1, 2, 3, 4}) cfgs.push_back({48, 0, 11904, 2, iss, 2048, IT, 0, 0, 0, 0});
+  cfgs.push_back({48, 0, 11904, 2, 3, 2048, IT, 16, 0, 0, 0});    // misaligned A
+  cfgs.push_back({48, 0, 11904, 2, 3, 2048, IT, 0, 27, 0, 0});    // B rotates over 27 weight slabs
+  cfgs.push_back({48, 0, 11904, 2, 3, 656, IT, 16, 27, 0, 0});    // both, row-pitch stride
+  cfgs.push_back({48, 0, 11904, 2, 3, 656, IT, 16, 27, 12, 0});   // + 12 warps streaming tcgen05.ld
+  cfgs.push_back({48, 0, 11904, 2, 3, 656, IT, 16, 27, 0, 2});    // + 2 warps streaming st.shared
+  cfgs.push_back({48, 0, 11904, 2, 3, 656, IT, 16, 27, 12, 2});   // both
+  cfgs.push_back({48, 0, 11904, 1, 3, 656, IT, 16, 27, 12, 2});   // both, one accumulator per issuer
+  cfgs.push_back({48, 0, 11904, 1, 1, 656, IT, 16, 27, 0, 0});    // single issuer
+  cfgs.push_back({240, 0, 11904, 1, 1, 2048, IT, 0, 0, 0, 0});    // N = 240 reference
+  printf("%4s %6s %6s %5s %7s %8s %5s %5s %3s %3s | %12s %14s %10s\n", "N", "layout", "lbo", "n_acc", "issuers", "a_stride", "a_off", "b_rot", "ld", "st", "cyc/MMA/iss",
          "cyc/MMA total", "ideal N/2");
   for (const Cfg& c : cfgs) {
     for (int rep = 0; rep < 2; ++rep) {
       cudaMemset(d_cycles, 0, 148 * 4 * sizeof(long long));
-      umma_bench_kernel<<<148, 160, 200 * 1024>>>(c, d_cycles);
+      umma_bench_kernel<<<148, 672, 200 * 1024>>>(c, d_cycles);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("config N=%d failed: %s\n", c.N, cudaGetErrorString(e)); return 1; }
     }
@@ -130,7 +159,7 @@ int main() {
     cudaMemcpy(h.data(), d_cycles, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     double mx = 0;
     for (int b = 0; b < 148; ++b) for (int i = 0; i < c.issuers; ++i) mx = mx > h[b * 4 + i] ? mx : (double)h[b * 4 + i];
-    printf("%4d %6d %6d %5d %7d %8d %5d | %12.1f %14.1f %10.1f\n", c.N, c.layout, c.lbo, c.n_acc, c.issuers, c.a_stride, c.a_off,
+    printf("%4d %6d %6d %5d %7d %8d %5d %5d %3d %3d | %12.1f %14.1f %10.1f\n", c.N, c.layout, c.lbo, c.n_acc, c.issuers, c.a_stride, c.a_off, c.b_rot, c.ld_warps, c.st_warps,
            mx / c.iters, mx / c.iters / c.issuers, c.N / 2.0);
   }
   return 0;
