@@ -136,12 +136,21 @@ __device__ __forceinline__ void tma_load_5d_hint(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(pol)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 int c2, int c3, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -198,6 +207,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+      ::"r"(taddr), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -517,6 +533,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcConvParams p
 
 }  // namespace kws
 #include "resnet_fused.cuh"
+#include "resnet_sweep.cuh"
 namespace kws {
 
 // ---------------------------------------------------------------------------------------------
@@ -730,6 +747,29 @@ __global__ void pack_conv3x3_tc_kernel(const float* __restrict__ w, const float*
   }
 }
 
+// torch [C][C][3][3] fp32 -> [NKC][3 dh][2 K halves][3 blocks][CP][8] bf16 for the column-sweep kernel
+// (resnet_sweep.cuh): block k of a (16-channel chunk, height tap) slab holds the width tap dw = 2 - k, so that
+// one N = 3*CP MMA on input column w feeds output columns w-d, w, w+d.  `in_scale` as above.
+__global__ void pack_conv3x3_sw_kernel(const float* __restrict__ w, const float* __restrict__ in_scale,
+                                       __nv_bfloat16* __restrict__ out, int C, int NKC) {
+  const int CP = 16 * NKC;
+  const int total = NKC * 3 * 2 * 3 * CP * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7;
+    int t = i >> 3;
+    const int co = t % CP; t /= CP;
+    const int blk = t % 3; t /= 3;
+    const int half = t & 1; t >>= 1;
+    const int dh = t % 3;
+    const int kc = t / 3;
+    const int ci = kc * 16 + half * 8 + e;
+    const int tap = dh * 3 + (2 - blk);
+    float v = (co < C && ci < C) ? w[((int64_t)co * C + ci) * 9 + tap] : 0.f;
+    if (in_scale != nullptr && ci < C) v *= in_scale[ci];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // Per-layer epilogue constants.  The activation stored by layer i is z_i = x_i - mean_i (the 1/sigma
 // factor is folded into layer i+1's weights).  The skip tensor x_{i-2} of an even layer is not stored:
 // it is z_{i-2} + mean_{i-2}, so z_i = ReLU(conv) + z_{i-2} + (mean_{i-2} - mean_i)   (resnet.py:49-55).
@@ -780,6 +820,7 @@ struct TcResNet {
   int n_sms = 148;
   void* blob = nullptr;
   std::vector<__nv_bfloat16*> wpack;        // per layer
+  std::vector<__nv_bfloat16*> wpack_sw;     // per layer, column-sweep layout (resnet_sweep.cuh)
   std::vector<float*> scale_p, shift_p;     // per layer, padded to CP: BN 1/sigma and the epilogue constant
   float* conv0_w = nullptr;                 // [C][9]
   float* out_w = nullptr;
@@ -792,6 +833,12 @@ struct TcResNet {
   std::tuple<int, int, const void*> fused_key{-1, -1, nullptr};
   TcFusedParams fused_prm{};
   int fused_smem = 0;
+  // column-sweep whole-network kernel (resnet_sweep.cuh), preferred when the map is tall enough
+  bool sweep_enabled = true;
+  void* sweep_dev = nullptr;   // [SwLayerDesc x n_layers][pad][CUtensorMap x n_layers]
+  std::tuple<int, int, const void*> sweep_key{-1, -1, nullptr};
+  SwParams sweep_prm{};
+  int sweep_smem = 0;
   // chunk pipelining: consecutive chunks run on `lanes` internal streams so that the prologue / tail of one
   // chunk's layer kernels overlaps the steady state of another's (each lane has its own activation buffers)
   int lanes = 1;
@@ -920,7 +967,7 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
     const int n = cfg.n_layers;
     const size_t w_bytes = round_up<size_t>((size_t)9 * p->NKC * 2 * p->CP * 16, 256);
     const size_t v_bytes = round_up<size_t>(p->CP * sizeof(float), 256);
-    const size_t total = n * (w_bytes + 2 * v_bytes) + round_up<size_t>(C * 9 * 4, 256) +
+    const size_t total = n * (2 * w_bytes + 2 * v_bytes) + round_up<size_t>(C * 9 * 4, 256) +
                          round_up<size_t>((size_t)cfg.n_labels * C * 4, 256) + round_up<size_t>(cfg.n_labels * 4, 256);
     if (cudaMalloc(&p->blob, total) != cudaSuccess) {
       set_error("tc_resnet_create: cudaMalloc(%zu) failed", total);
@@ -930,6 +977,7 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
     char* b = static_cast<char*>(p->blob);
     for (int i = 0; i < n; ++i) {
       p->wpack.push_back(reinterpret_cast<__nv_bfloat16*>(b)); b += w_bytes;
+      p->wpack_sw.push_back(reinterpret_cast<__nv_bfloat16*>(b)); b += w_bytes;
       p->scale_p.push_back(reinterpret_cast<float*>(b)); b += v_bytes;
       p->shift_p.push_back(reinterpret_cast<float*>(b)); b += v_bytes;
     }
@@ -938,6 +986,8 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
     p->out_b = reinterpret_cast<float*>(b);
     const char* fenv = std::getenv("HONK2_TC_FUSED");
     p->fused_enabled = fenv == nullptr || std::atoi(fenv) != 0;
+    const char* senv = std::getenv("HONK2_TC_SWEEP");
+    p->sweep_enabled = senv == nullptr || std::atoi(senv) != 0;
     const char* env = std::getenv("HONK2_TC_LANES");
     p->lanes = env ? std::max(1, std::min(kTcMaxLanes, std::atoi(env))) : 2;
     bool ok = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) == cudaSuccess;
@@ -958,6 +1008,7 @@ void tc_resnet_destroy(TcResNet* p) {
   if (!p) return;
   if (p->blob) cudaFree(p->blob);
   if (p->fused_dev) cudaFree(p->fused_dev);
+  if (p->sweep_dev) cudaFree(p->sweep_dev);
   for (int l = 0; l < kTcMaxLanes; ++l) {
     if (p->lane_stream[l]) cudaStreamDestroy(p->lane_stream[l]);
     if (p->ev_done[l]) cudaEventDestroy(p->ev_done[l]);
@@ -973,6 +1024,9 @@ int tc_resnet_set_weights(TcResNet* p, const kws_resnet_weights& w, float* const
   for (int i = 0; i < n; ++i) {
     pack_conv3x3_tc_kernel<<<ceil_div(9 * p->NKC * 2 * p->CP * 8, 256), 256, 0, st>>>(
         w.conv_w[i], i > 0 ? bn_scale[i - 1] : nullptr, p->wpack[i], C, p->NKC);
+    KWS_CUDA(cudaGetLastError());
+    pack_conv3x3_sw_kernel<<<ceil_div(9 * p->NKC * 2 * p->CP * 8, 256), 256, 0, st>>>(
+        w.conv_w[i], i > 0 ? bn_scale[i - 1] : nullptr, p->wpack_sw[i], C, p->NKC);
     KWS_CUDA(cudaGetLastError());
     // layer number i+1 is even and > 2  <=>  its skip comes from a normalised layer (i-1 in 0-based terms)
     const float* skip_mean = ((i + 1) % 2 == 0 && i >= 3) ? w.bn_mean[i - 2] : nullptr;
@@ -1202,6 +1256,152 @@ static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat
   }
 }
 
+// ---- column-sweep whole-network kernel (resnet_sweep.cuh): plan, tables, launch --------------------
+struct TcSweepPlan {
+  bool ok = false;
+  int n_slots = 0, n_strips = 0, smem_total = 0, n_stages = 0;
+  int w_off[2] = {0, 0}, ring_off = 0, slot_bytes = 0;
+  std::vector<int> dil;
+};
+
+static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W) {
+  TcSweepPlan f;
+  const kws_resnet_config& c = p->cfg;
+  if (!p->sweep_enabled || c.n_layers < 1 || c.n_layers > kFusedMaxLayers || c.n_labels > 4096) return f;
+  if (W < 1 || W > kSwMaxW || H < 1) return f;
+  f.n_strips = ceil_div(H, 128);
+  // the 128 lanes of an MMA are 128 rows of one column: short maps (res8 / res26 after pooling) would leave
+  // most lanes idle and stay on the position-major kernel
+  static const int min_pct = [] { const char* e = std::getenv("HONK2_TC_SWEEP_MINPCT"); return e ? std::atoi(e) : 60; }();
+  if (H * 100 < f.n_strips * 128 * min_pct) return f;
+  int dmax = 1;
+  for (int i = 1; i <= c.n_layers; ++i) {
+    const int d = c.use_dilation ? (1 << ((i - 1) / 3)) : 1;
+    if (d > 64) return f;   // TMA box of 128 + 2d rows must stay <= 256
+    dmax = std::max(dmax, d);
+    f.dil.push_back(d);
+  }
+  f.n_slots = p->n_sms;
+  const int w_bytes = 9 * p->NKC * 2 * p->CP * 16;
+  f.w_off[0] = kSwCtrlBytes;
+  f.w_off[1] = f.w_off[0] + round_up(w_bytes, 128);
+  f.ring_off = round_up(f.w_off[1] + w_bytes, 1024);
+  f.slot_bytes = round_up(p->NP * ((128 + 2 * dmax + 7) & ~7) * 16, 128);
+  static const int max_stages = [] { const char* e = std::getenv("HONK2_TC_SWEEP_STAGES"); return e ? std::atoi(e) : kSwMaxStages; }();
+  f.n_stages = std::min(std::min(kSwMaxStages, max_stages), (227 * 1024 - f.ring_off) / f.slot_bytes);
+  if (f.n_stages < 3) return f;
+  f.smem_total = f.ring_off + f.n_stages * f.slot_bytes;
+  f.ok = true;
+  return f;
+}
+
+static size_t tc_sweep_ws_bytes(const TcResNet* p, const TcSweepPlan& f, int H, int W, size_t* buf_out) {
+  const size_t buf = round_up<size_t>((size_t)f.n_slots * p->NP * H * W * 16, 1024);
+  if (buf_out) *buf_out = buf;
+  return 2 * buf;
+}
+
+template <int NKC>
+static int tc_launch_sweep(const SwParams& prm, int grid, int smem, cudaStream_t st) {
+  KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  resnet_tc_sweep_kernel<NKC><<<grid, sw_threads(NKC), smem, st>>>(prm);
+  KWS_CHECK_LAUNCH();
+  return KWS_OK;
+}
+
+static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat, int64_t B, int T, int F, int H, int W,
+                            float* logits, void* ws, LaunchProfiler* prof, cudaStream_t st) {
+  const kws_resnet_config& c = p->cfg;
+  size_t buf = 0;
+  tc_sweep_ws_bytes(p, f, H, W, &buf);
+  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws));
+  __nv_bfloat16* Q = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + buf);
+  const auto key = std::make_tuple(T, F, (const void*)ws);
+  if (p->sweep_key != key) {
+    const int n = c.n_layers;
+    const size_t maps_off = 0;
+    const size_t total = sizeof(CUtensorMap) * n;
+    std::vector<unsigned char> host(total, 0);
+    for (int i = 1; i <= n; ++i) {
+      const int d = f.dil[i - 1];
+      const int box_rows = (128 + 2 * d + 7) & ~7;
+      const bool in_q = (i % 2 == 0);
+      // dims: 8 channels, H rows, W columns, planes; box: {8, 128 + 2d rows, 1 column, NP planes}
+      CUtensorMap m;
+      const cuuint64_t dims[4] = {8, (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)f.n_slots * p->NP};
+      const cuuint64_t strides[3] = {16, (cuuint64_t)H * 16, (cuuint64_t)H * W * 16};
+      const cuuint32_t box[4] = {8, (cuuint32_t)box_rows, 1, (cuuint32_t)p->NP};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in_q ? (void*)Q : (void*)P, dims, strides, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for the column-sweep map H=%d W=%d box_rows=%d", (int)r, H, W, box_rows);
+        return KWS_ERR_CUDA;
+      }
+      memcpy(host.data() + maps_off + sizeof(CUtensorMap) * (i - 1), &m, sizeof(m));
+    }
+    if (p->sweep_dev) { KWS_CUDA(cudaStreamSynchronize(st)); KWS_CUDA(cudaFree(p->sweep_dev)); p->sweep_dev = nullptr; }
+    KWS_CUDA(cudaMalloc(&p->sweep_dev, total));
+    KWS_CUDA(cudaMemcpyAsync(p->sweep_dev, host.data(), total, cudaMemcpyHostToDevice, st));
+    KWS_CUDA(cudaStreamSynchronize(st));   // `host` goes out of scope; this happens once per shape
+    SwParams& q = p->sweep_prm;
+    q = SwParams{};
+    q.maps = reinterpret_cast<const CUtensorMap*>(static_cast<char*>(p->sweep_dev) + maps_off);
+    q.wpack0 = reinterpret_cast<const unsigned char*>(p->wpack_sw[0]);
+    q.kconst0 = reinterpret_cast<const unsigned char*>(p->shift_p[0]);
+    q.layer_stride = n > 1 ? (int64_t)(reinterpret_cast<const unsigned char*>(p->wpack_sw[1]) - q.wpack0) : 0;
+    q.use_dilation = c.use_dilation ? 1 : 0;
+    q.conv0_w = p->conv0_w;
+    q.last_scale = p->scale_p[n - 1];
+    q.out_w = p->out_w;
+    q.out_b = p->out_b;
+    q.P = P; q.Q = Q;
+    q.n_layers = n; q.C = c.n_maps; q.n_labels = c.n_labels; q.T = T; q.F = F;
+    q.ph = c.pool_h > 0 ? c.pool_h : 1; q.pw = c.pool_w > 0 ? c.pool_w : 1;
+    q.H = H; q.W = W; q.n_strips = f.n_strips;
+    q.smem_w_off[0] = f.w_off[0]; q.smem_w_off[1] = f.w_off[1];
+    q.smem_ring_off = f.ring_off; q.ring_slot_bytes = f.slot_bytes; q.n_stages = f.n_stages;
+    {
+      const char* e = std::getenv("HONK2_TC_L2POLICY");
+      q.l2_policy = e ? std::atoi(e) : 1;
+    }
+    p->sweep_smem = f.smem_total;
+    p->sweep_key = key;
+  }
+  if (prof) prof->tick(0, st);   // the whole network is one launch: it IS the dominant kernel
+  SwParams prm = p->sweep_prm;
+  prm.feat = feat;
+  prm.logits = logits;
+  prm.B = B;
+  const int grid = (int)std::min<int64_t>(f.n_slots, B);
+  static const bool dbg_on = [] { const char* e = std::getenv("HONK2_TC_DEBUG"); return e && std::atoi(e) != 0; }();
+  static long long* dbg_buf = nullptr;
+  if (dbg_on) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
+    prm.debug = dbg_buf;
+  }
+  struct DbgPrint {
+    long long* buf; cudaStream_t st;
+    ~DbgPrint() {
+      if (!buf) return;
+      long long h[8];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+      const double tot = (double)(h[0] + h[1] + h[2] + h[3]);
+      fprintf(stderr, "[sweep dbg] issuer of CTA 0, %lld utterances, cycles: weights/conv_0 wait %.1f%%, accumulator-free wait %.1f%%, "
+              "TMA-data wait %.1f%%, issuing MMAs %.1f%% (total %.0f, %.0f per utterance)\n",
+              h[4], 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, tot, tot / (double)std::max(1ll, h[4]));
+    }
+  } dbg_print{dbg_on ? dbg_buf : nullptr, st};
+  switch (p->NKC) {
+    case 1: return tc_launch_sweep<1>(prm, grid, p->sweep_smem, st);
+    case 2: return tc_launch_sweep<2>(prm, grid, p->sweep_smem, st);
+    case 3: return tc_launch_sweep<3>(prm, grid, p->sweep_smem, st);
+    default: return tc_launch_sweep<4>(prm, grid, p->sweep_smem, st);
+  }
+}
+
 size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int chunk) {
   if (!p || !p->supported) return 0;
   int H, W;
@@ -1211,7 +1411,10 @@ size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int
   const size_t layered = p->lanes * tc_lane_bytes(p, c, H, W, nullptr);
   const TcFusedPlan f = tc_fused_plan(p, H, W);
   // the layer-per-launch path stays available (profiling, shapes the fused kernel cannot stage)
-  return f.ok ? std::max(layered, tc_fused_ws_bytes(p, f, W, nullptr)) : layered;
+  size_t need = f.ok ? std::max(layered, tc_fused_ws_bytes(p, f, W, nullptr)) : layered;
+  const TcSweepPlan sp = tc_sweep_plan(p, H, W);
+  if (sp.ok) need = std::max(need, tc_sweep_ws_bytes(p, sp, H, W, nullptr));
+  return need;
 }
 
 template <int NKC, bool HAS_PREV, bool DO_POOL>
@@ -1265,8 +1468,12 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
   }
   {
     // whole-network persistent kernel unless per-launch profiling was requested
-    const TcFusedPlan f = tc_fused_plan(p, H, W);
     static const bool prof_layered = [] { const char* e = std::getenv("HONK2_TC_PROFILE_LAYERED"); return e && std::atoi(e) != 0; }();
+    const TcSweepPlan sp = tc_sweep_plan(p, H, W);
+    if (sp.ok && !(prof && prof->enabled && prof_layered)) {
+      return tc_sweep_forward(p, sp, feat, B, T, F, H, W, logits, ws, prof, st);
+    }
+    const TcFusedPlan f = tc_fused_plan(p, H, W);
     if (f.ok && !(prof && prof->enabled && prof_layered)) {
       return tc_fused_forward(p, f, feat, B, T, F, H, W, logits, ws, prof, st);
     }
