@@ -68,6 +68,38 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with an explicit suspend-time hint (ns): the thread sleeps in hardware until the phase completes or
+// the time is up, instead of re-issuing the poll (and competing with other warps for issue slots)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (clock64() - t0 > kSpinLimitCycles) __trap();
+  }
+}
+// Wait with few instructions per poll (for the MMA issuers, whose instruction count is the bottleneck): the
+// hardware suspends the thread until the phase completes or the hint elapses; the watchdog is read every 256 polls.
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = 0;
+  for (uint32_t it = 1; !mbar_try_wait_hint(bar, parity, 100000u); ++it) {
+    if ((it & 255u) == 0u) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > kSpinLimitCycles) __trap();
+    }
+  }
+}
 // Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -88,6 +120,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
@@ -1303,8 +1340,13 @@ static size_t tc_sweep_ws_bytes(const TcResNet* p, const TcSweepPlan& f, int H, 
 
 template <int NKC>
 static int tc_launch_sweep(const SwParams& prm, int grid, int smem, cudaStream_t st) {
-  KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  resnet_tc_sweep_kernel<NKC><<<grid, sw_threads(NKC), smem, st>>>(prm);
+  if (prm.debug != nullptr) {
+    KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    resnet_tc_sweep_kernel<NKC, true><<<grid, sw_threads(NKC), smem, st>>>(prm);
+  } else {
+    KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    resnet_tc_sweep_kernel<NKC, false><<<grid, sw_threads(NKC), smem, st>>>(prm);
+  }
   KWS_CHECK_LAUNCH();
   return KWS_OK;
 }
@@ -1360,11 +1402,22 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
     q.n_layers = n; q.C = c.n_maps; q.n_labels = c.n_labels; q.T = T; q.F = F;
     q.ph = c.pool_h > 0 ? c.pool_h : 1; q.pw = c.pool_w > 0 ? c.pool_w : 1;
     q.H = H; q.W = W; q.n_strips = f.n_strips;
+    {
+      static const bool bulk_on = [] { const char* e = std::getenv("HONK2_TC_SWEEP_BULK"); return e == nullptr || std::atoi(e) != 0; }();
+      int dmax = 1;
+      for (int dd : f.dil) dmax = std::max(dmax, dd);
+      q.dmax = dmax;
+      q.bulk_rows = (bulk_on && f.n_strips == 1) ? H : 0;
+    }
     q.smem_w_off[0] = f.w_off[0]; q.smem_w_off[1] = f.w_off[1];
     q.smem_ring_off = f.ring_off; q.ring_slot_bytes = f.slot_bytes; q.n_stages = f.n_stages;
     {
       const char* e = std::getenv("HONK2_TC_L2POLICY");
       q.l2_policy = e ? std::atoi(e) : 1;
+    }
+    {
+      const char* e = std::getenv("HONK2_TC_ISSUE_STYLE");
+      q.issue_style = e ? std::atoi(e) : 0;
     }
     p->sweep_smem = f.smem_total;
     p->sweep_key = key;
@@ -1378,20 +1431,26 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
   static const bool dbg_on = [] { const char* e = std::getenv("HONK2_TC_DEBUG"); return e && std::atoi(e) != 0; }();
   static long long* dbg_buf = nullptr;
   if (dbg_on) {
-    if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(long long));
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
     prm.debug = dbg_buf;
   }
   struct DbgPrint {
     long long* buf; cudaStream_t st;
     ~DbgPrint() {
       if (!buf) return;
-      long long h[8];
+      long long h[16];
       cudaStreamSynchronize(st);
       cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
-      const double tot = (double)(h[0] + h[1] + h[2] + h[3]);
-      fprintf(stderr, "[sweep dbg] issuer of CTA 0, %lld utterances, cycles: weights/conv_0 wait %.1f%%, accumulator-free wait %.1f%%, "
-              "TMA-data wait %.1f%%, issuing MMAs %.1f%% (total %.0f, %.0f per utterance)\n",
-              h[4], 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, tot, tot / (double)std::max(1ll, h[4]));
+      const double tot = (double)(h[0] + h[1] + h[2] + h[3] + h[5] + h[6] + h[7]);
+      fprintf(stderr, "[sweep dbg] issuer 0 of CTA 0, %lld utterances, cycles: weights wait %.1f%%, accumulator-free wait %.1f%%, "
+              "TMA-data wait %.1f%%, utterance boundary (tail + conv_0 + first load) %.1f%%, issuing own steps %.1f%%, first loop top after an own step %.1f%%, counting along %.1f%% "
+              "(total %.0f, %.0f per utterance)\n",
+              h[4], 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[5] / tot, 100 * h[3] / tot, 100 * h[7] / tot, 100 * h[6] / tot, tot,
+              tot / (double)std::max(1ll, h[4]));
+      const double et = (double)(h[8] + h[9] + h[10] + h[11] + h[12]);
+      fprintf(stderr, "[sweep dbg] epilogue warp 0 of CTA 0: waiting for accumulators %.1f%%, TMEM load + re-zero %.1f%%, publishing the "
+              "previous column %.1f%%, math + stores (+ guard, tail) %.1f%%, conv_0 %.1f%% (total %.0f)\n",
+              100 * h[8] / et, 100 * h[9] / et, 100 * h[10] / et, 100 * h[11] / et, 100 * h[12] / et, et);
     }
   } dbg_print{dbg_on ? dbg_buf : nullptr, st};
   switch (p->NKC) {

@@ -27,10 +27,15 @@
 // layer l (col_done), the epilogue of layer l+1 starts storing only after every MMA of layer l has
 // retired (layer_done: the two layers ping-pong the same buffers), weights are double buffered.
 #pragma once
+#include <type_traits>
 
 namespace kws {
 
-constexpr int kSwFrontWarps = 4;    // warp 0: TMA producer, warps 1-3: MMA issuers (epilogue warp % 4 stays the TMEM lane quarter)
+// Warp roles: warps 0 .. 4*NKC-1 epilogue (warp % 4 = TMEM lane quarter), then one TMA producer warp and three
+// MMA issuer warps.  The front-end warps have the HIGHEST warp ids on purpose: the SM's warp arbiter prefers
+// higher ids, and the epilogue warps spend half their time polling barriers; with the issuers at the low ids
+// every instruction of the (latency-critical) issue loops waited behind those polls.
+constexpr int kSwFrontWarps = 4;
 constexpr int kSwIssuers = 3;       // issuer m issues the MMAs of height tap dh = m
 constexpr int kSwMaxStages = 12;
 constexpr int kSwMaxRing = 32;
@@ -50,7 +55,8 @@ constexpr int kSwBarLayer = kSwBarWfull + 16;                  // [2]  all MMAs 
 constexpr int kSwBarConv0 = kSwBarLayer + 16;                  // [1]  conv_0 output stored
 constexpr int kSwBarCol = kSwBarConv0 + 8;                     // [2][kSwMaxW]  column stored by every epilogue warp
 constexpr int kSwTmemSlot = kSwBarCol + 8 * 2 * kSwMaxW;       // u32
-constexpr int kSwPool = round_up(kSwTmemSlot + 4, 128);        // [64] f32 pooled sums
+constexpr int kSwZero = kSwTmemSlot + 4;                       // u32, always 0 (see the MMA issuers)
+constexpr int kSwPool = round_up(kSwZero + 4, 128);            // [64] f32 pooled sums
 constexpr int kSwW0 = kSwPool + 256;                           // [64][12] f32 conv_0 weights
 constexpr int kSwCtrlBytes = round_up(kSwW0 + 64 * 12 * 4, 1024);
 
@@ -77,10 +83,14 @@ struct SwParams {
   int n_strips;                 // ceil(H / 128)
   int smem_w_off[2], smem_ring_off, ring_slot_bytes, n_stages;
   int l2_policy;
+  int bulk_rows;                // > 0 (single-strip maps): columns are staged with 1-D bulk copies of bulk_rows = H rows per plane
+                                //   into a fixed [plane][128 + 2 dmax] slot whose pad rows stay zero; 0: TMA tensor boxes
+  int dmax;                     // largest dilation of the network (bulk path: data row h sits at slot row dmax + h)
+  int issue_style;              // 0: MMA operands in uniform registers, 1: ordinary registers + R2UR (experiments)
   long long* debug;             // optional [8] cycle counters of CTA 0's issuer
 };
 
-template <int NKC>
+template <int NKC, bool DBG>
 __global__ void __launch_bounds__(sw_threads(NKC), 1)
 resnet_tc_sweep_kernel(const SwParams p) {
   constexpr int kEpiWarps = sw_epi_warps(NKC);
@@ -115,7 +125,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), kSwIssuers); }
+    for (int s = 0; s < p.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NB; ++a) { mbar_init(tfull_bar(a), kSwIssuers); mbar_init(tempty_bar(a), kEpiWarps); }
     for (int i = 0; i < 2; ++i) { mbar_init(wfull_bar(i), 1); mbar_init(layer_bar(i), kSwIssuers); }
     mbar_init(conv0_bar, kEpiWarps);
@@ -123,20 +133,28 @@ resnet_tc_sweep_kernel(const SwParams p) {
       for (int w = 0; w < W; ++w) mbar_init(col_bar(par, w), (uint32_t)(kEpiWarps * n_strips));
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (threadIdx.x == 32) *reinterpret_cast<volatile uint32_t*>(smem + kSwZero) = 0u;
+  if (warp == kEpiWarps + 1) tmem_alloc(smem_u32(tmem_slot), 512);
   for (int i = threadIdx.x; i < CP * 12; i += sw_threads(NKC)) {
     const int c = i / 12, k = i - c * 12;
     s_w0[i] = (k < 9 && c < p.C) ? p.conv0_w[c * 9 + k] : 0.f;
   }
   for (int i = threadIdx.x; i < CP; i += sw_threads(NKC)) s_pool[i] = 0.f;
+  if (p.bulk_rows > 0) {
+    // bulk-copy staging: the pad rows above and below the map are never written again and supply the zero padding
+    uint4* ring = reinterpret_cast<uint4*>(smem + p.smem_ring_off);
+    const int n16 = p.n_stages * (p.ring_slot_bytes >> 4);
+    for (int i = threadIdx.x; i < n16; i += sw_threads(NKC)) ring[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();   // generic-proxy zeros -> visible to the tensor core's (async proxy) operand reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Every MMA accumulates (three issuer warps feed the same accumulators, in no particular order), so the ring
   // starts zeroed and the epilogue re-zeroes each block right after reading it.
-  if (warp >= kSwFrontWarps) {
-    const int q = warp & 3, j = (warp - kSwFrontWarps) >> 2;
+  if (warp < kEpiWarps) {
+    const int q = warp & 3, j = warp >> 2;
     for (int a = 0; a < NB; ++a) tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * CP + 16 * j));
     tmem_st_wait();
   }
@@ -153,9 +171,12 @@ resnet_tc_sweep_kernel(const SwParams p) {
   const uint64_t pol_stream = l2_policy_evict_first();
 
   auto layer_dil = [&](int l) { return p.use_dilation ? (1 << (l / 3)) : 1; };
-  auto box_rows_of = [&](int d) { return (128 + 2 * d + 7) & ~7; };   // plane pitch in smem stays a multiple of 128 B
+  // rows per plane of a staged column = plane pitch in shared memory (kept a multiple of 8 rows = 128 B)
+  auto box_rows_of = [&](int d) { return p.bulk_rows > 0 ? 128 + 2 * p.dmax : ((128 + 2 * d + 7) & ~7); };
+  // slot row that the height tap dh = 0 of output row 0 reads
+  auto row0_of = [&](int d) { return p.bulk_rows > 0 ? p.dmax - d : 0; };
 
-  if (warp == 0) {
+  if (warp == kEpiWarps) {
     // ========================================= TMA producer =========================================
     // The whole warp walks the (warp-uniform) schedule; one elected lane issues the copies.
     const bool leader = elect_one();
@@ -173,7 +194,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
           const int d = layer_dil(l), box_rows = box_rows_of(d);
           const int n_runs = d < W ? d : W;
           const uint32_t tx = (uint32_t)(NP * box_rows * 16);
-          const uint64_t pol = (l & 1) ? pol_stream : pol_keep;
+          const bool in_q = (l & 1) != 0;
+          const uint64_t pol = in_q ? pol_stream : pol_keep;
           bool w_pending = seq + 1 < n_seq;
           auto request_weights = [&]() {
             // buffer (seq+1)&1 was read by the MMAs of layer seq-1: wait until they have retired
@@ -196,9 +218,19 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 if (w_pending && step == kSwWeightStep) request_weights();
                 if (l > 0) mbar_wait(col_bar(prev_par, w), prev_phase);   // column w of the previous layer is stored
                 mbar_wait(empty_bar(stage), sphase ^ 1);
-                if (leader) {
+                const uint32_t dst = sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes;
+                if (p.bulk_rows > 0) {
+                  // one contiguous H x 16 B run per 8-channel plane (a TMA box with 16-byte rows fetches a whole
+                  // 32-byte sector per row: 2.6x the bytes, measured with ncu)
+                  const uint32_t bytes = (uint32_t)p.bulk_rows * 16u;
+                  if (leader) mbar_expect_tx(full_bar(stage), bytes * NP);
+                  __syncwarp();
+                  if (lane < NP) {
+                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)lane * plane_stride + (int64_t)w * H;
+                    bulk_load_hint(dst + (uint32_t)(lane * box_rows + p.dmax) * 16u, src, bytes, full_bar(stage), pol);
+                  }
+                } else if (leader) {
                   mbar_expect_tx(full_bar(stage), tx);
-                  const uint32_t dst = sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes;
                   if (use_pol) tma_load_4d_hint(dst, map, full_bar(stage), 0, s * 128 - d, w, (int)blockIdx.x * NP, pol);
                   else tma_load_4d(dst, map, full_bar(stage), 0, s * 128 - d, w, (int)blockIdx.x * NP);
                 }
@@ -209,28 +241,44 @@ resnet_tc_sweep_kernel(const SwParams p) {
       }
     }
     __syncwarp();
-  } else if (warp <= kSwIssuers) {
+  } else if (warp > kEpiWarps) {
     // ========================================= MMA issuers (3 warps) =========================================
-    // One N = 3*CP MMA lasts 72 tensor-pipe cycles but a single thread issues one only every ~110 cycles
-    // (tools/umma_bench3.cu), so the nine MMAs of a step are dealt to three warps: issuer m takes height tap
-    // dh = m of every 16-channel chunk.  All of them accumulate into the same blocks, which is order independent
-    // because nothing overwrites (tools/umma_bench2.cu: concurrent accumulation from two warps is exact).
-    // Operands are derived from kernel parameters and warp-uniform counters only, so the issue loop stays on
-    // the uniform datapath; all lanes walk the schedule and wait on the barriers, one elected lane issues.
-    const int me = warp - 1;
-    const bool leader = elect_one();
-    if (n_seq > 0) {
+    // Issuer m owns every third STEP: it waits for the step's staged column and for the ring slots of the step's
+    // window, issues the 3*NKC MMAs of the step (twice as many, half as wide, when the window wraps around the
+    // ring) and commits; for the other two steps it only advances its counters.  While one issuer is inside its
+    // burst the next one has already prepared its operands and queues right behind it.  All MMAs accumulate (the
+    // ring blocks are zeroed by the epilogue), so the order in which the three warps' MMAs reach the tensor pipe
+    // does not matter (tools/umma_bench2/4: concurrent accumulation from several warps into one accumulator is
+    // exact and runs at the pipe rate).
+    //
+    // What limits this role is the INSTRUCTION COUNT of its single worker lane (ncu: ~5 cycles per instruction in
+    // this branchy scalar code, the MMA instructions themselves are 3 % of its time), so the step is kept lean: ring
+    // slots advance by increments (no divisions), the cycle accounting is compiled out unless DBG, barrier polls use
+    // the hardware suspend hint, and the MMA burst is straight-line code without predicated-off instructions.
+    //
+    // An output block receives MMAs from the steps of its three neighbouring input columns, i.e. from all three
+    // issuers: tfull counts three arrivals (each issuer commits on every block of its window; the run's first and
+    // last block, which have only two contributing steps, get a plain arrival from the issuer of the edge step),
+    // and every issuer waits for the ring slot of every block of its window to be drained, not only the fresh one,
+    // because nothing orders the issuers among themselves.
+    const int me = warp - kEpiWarps - 1;
+    const uint32_t nz = p.issue_style ? *reinterpret_cast<volatile uint32_t*>(smem + kSwZero) : 0u;
+    if (lane == 0 && n_seq > 0) {
       int stage = 0;
       uint32_t sphase = 0;
-      int run_pos = 0;          // ring position of output column 0 of the current run
-      uint32_t run_par = 0;     // use parity of that ring slot
+      int owner = 0;            // issuer of the current step (global step counter mod 3)
+      int sl = 0;               // ring slot of the output block of the CURRENT step's own column
+      uint32_t pr = 0;          // use parity of that slot
       constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
       constexpr uint32_t idesc0 = umma_idesc(128, 0);
       constexpr uint32_t idesc_blk = (uint32_t)(CP >> 3) << 17;   // one more block of CP columns
       constexpr uint32_t b_lbo = ((uint32_t)(W_LBO >> 4) & 0x3FFFu) << 16;
       constexpr uint32_t blk16 = BLK_BYTES >> 4;
-      long long dbg_full = 0, dbg_tempty = 0, dbg_issue = 0, dbg_w = 0, dbg_t = clock64();
-      const bool dbg = p.debug != nullptr && blockIdx.x == 0 && me == 0;
+      long long dbg_full = 0, dbg_tempty = 0, dbg_issue = 0, dbg_w = 0, dbg_utt = 0, dbg_other = 0, dbg_t = DBG ? clock64() : 0;
+      const bool dbg = DBG && p.debug != nullptr && blockIdx.x == 0 && me == 0;
+      auto stamp = [&](long long& bucket) {
+        if constexpr (DBG) { if (dbg) { const long long t = clock64(); bucket += t - dbg_t; dbg_t = t; } }
+      };
       int64_t seq = 0;
       for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
         for (int l = 0; l < n_layers; ++l, ++seq) {
@@ -239,77 +287,98 @@ resnet_tc_sweep_kernel(const SwParams p) {
           const int cur = (int)(seq & 1);
           const uint32_t plane16 = (uint32_t)box_rows;                       // plane pitch in 16-byte units
           const uint32_t a_lbo = (plane16 & 0x3FFFu) << 16;
-          const uint32_t w16 = ((sbase + p.smem_w_off[cur]) >> 4) + (uint32_t)((me * W_SLAB) >> 4);   // slab (kc = 0, dh = me)
-          const uint32_t a_off = (uint32_t)(me * d);                         // row shift of height tap dh = me
-          mbar_wait(wfull_bar(cur), (uint32_t)((seq >> 1) & 1));
-          if (dbg) { const long long t = clock64(); dbg_w += t - dbg_t; dbg_t = t; }
+          const uint32_t w16 = ((sbase + p.smem_w_off[cur]) >> 4) + nz;
+          const uint32_t row0 = (uint32_t)row0_of(d);
+          stamp(dbg_other);
+          mbar_wait_lean(wfull_bar(cur), (uint32_t)((seq >> 1) & 1));
+          stamp(dbg_w);
           for (int s = 0; s < n_strips; ++s)
             for (int r = 0; r < n_runs; ++r) {
               const int Lr = (W - r + d - 1) / d;   // output columns of this run
               for (int i = 0; i < Lr; ++i) {
-                // this step's output blocks: columns o_lo .. o_hi of the run, n of them, ring-contiguous from p0
-                const int o_lo = i > 0 ? i - 1 : 0, o_hi = i + 1 < Lr ? i + 1 : Lr - 1;
-                const int n = o_hi - o_lo + 1;
-                const int t0 = run_pos + o_lo, q0 = t0 / NB, p0 = t0 - q0 * NB;
-                const int wrap_at = NB - p0 < n ? NB - p0 : n;              // blocks before the ring wraps
-                const int fresh_from = i == 0 ? 0 : (i + 1 < Lr ? n - 1 : n);   // first block nobody has written yet
-                const int blk0 = o_lo - (i - 1);                             // weight block of the first output block
-                // a fresh block reuses a ring slot: the epilogue must have drained and re-zeroed it
-                for (int k = fresh_from; k < n; ++k) {
-                  const int t = t0 + k, qd = t / NB;
-                  mbar_wait(tempty_bar(t - qd * NB), (run_par ^ (uint32_t)(qd & 1)) ^ 1u);
-                }
-                if (dbg) { const long long t = clock64(); dbg_tempty += t - dbg_t; dbg_t = t; }
-                mbar_wait(full_bar(stage), sphase);
-                tc_fence_after();
-                if (dbg) { const long long t = clock64(); dbg_full += t - dbg_t; dbg_t = t; }
-                const uint32_t a16 = ((sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes) >> 4) + a_off;
-                // the (at most two) ring-contiguous pieces of the window
-                const uint32_t d1 = tmem_base + (uint32_t)(p0 * CP), bo1 = (uint32_t)blk0 * blk16;
-                const uint32_t id1 = idesc0 + (uint32_t)wrap_at * idesc_blk;
-                const bool two = wrap_at < n;
-                const uint32_t d2 = tmem_base, bo2 = (uint32_t)(blk0 + wrap_at) * blk16;
-                const uint32_t id2 = idesc0 + (uint32_t)(n - wrap_at) * idesc_blk;
-                if (leader) {
+                if (owner == me) {
+                  // window = output blocks of columns i-1 (if any), i, i+1 (if any): n blocks, ring-contiguous from p0
+                  const bool lo = i > 0, hi_ = i + 1 < Lr;
+                  const int s_lo = sl > 0 ? sl - 1 : NB - 1, s_hi = sl + 1 < NB ? sl + 1 : 0;
+                  const uint32_t par_lo = pr ^ (sl == 0 ? 1u : 0u), par_hi = pr ^ (sl + 1 == NB ? 1u : 0u);
+                  const int p0 = lo ? s_lo : sl;
+                  const int n = 1 + (lo ? 1 : 0) + (hi_ ? 1 : 0);
+                  const int wrap_at = NB - p0 < n ? NB - p0 : n;              // blocks before the ring wraps
+                  const int blk0 = lo ? 0 : 1;                                 // weight block of the first window block
+                  stamp(dbg_other);
+                  // the epilogue must have drained and re-zeroed the previous use of every slot of the window
+                  if (lo) mbar_wait_lean(tempty_bar(s_lo), par_lo ^ 1u);
+                  mbar_wait_lean(tempty_bar(sl), pr ^ 1u);
+                  if (hi_) mbar_wait_lean(tempty_bar(s_hi), par_hi ^ 1u);
+                  stamp(dbg_tempty);
+                  mbar_wait_lean(full_bar(stage), sphase);
+                  tc_fence_after();
+                  if constexpr (DBG) { if (l == 0 && s == 0 && r == 0 && i < kSwIssuers) stamp(dbg_utt); else stamp(dbg_full); }
+                  // All operands of the step are computed BEFORE the burst, and the burst is straight-line code
+                  // without predicated-off MMAs (separate path for the wrapped window).
+                  const uint32_t a16 = ((sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes) >> 4) + row0 + nz;
+                  const uint32_t d1 = tmem_base + (uint32_t)(p0 * CP);
+                  const uint32_t id1 = idesc0 + (uint32_t)wrap_at * idesc_blk;
+                  uint32_t al[3 * NKC], bl[3 * NKC];
 #pragma unroll
-                  for (int kc = 0; kc < NKC; ++kc) {
-                    const uint32_t a_lo = ((a16 + (uint32_t)(2 * kc) * plane16) & 0x3FFFu) | a_lbo;
-                    const uint32_t b16 = w16 + (uint32_t)((kc * 3 * W_SLAB) >> 4);
-                    umma_f16_lohi<true>(d1, a_lo, ((b16 + bo1) & 0x3FFFu) | b_lbo, desc_hi, id1);
-                    if (two) umma_f16_lohi<true>(d2, a_lo, ((b16 + bo2) & 0x3FFFu) | b_lbo, desc_hi, id2);
+                  for (int kc = 0; kc < NKC; ++kc)
+#pragma unroll
+                    for (int dh = 0; dh < 3; ++dh) {
+                      al[kc * 3 + dh] = ((a16 + (uint32_t)(2 * kc) * plane16 + (uint32_t)(dh * d)) & 0x3FFFu) | a_lbo;
+                      bl[kc * 3 + dh] = ((w16 + (uint32_t)(((kc * 3 + dh) * W_SLAB) >> 4) + (uint32_t)blk0 * blk16) & 0x3FFFu) | b_lbo;
+                    }
+                  if (wrap_at == n) {
+#pragma unroll
+                    for (int k = 0; k < 3 * NKC; ++k) umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
+                  } else {
+                    // the window wraps around the ring: first wrap_at blocks at p0, the rest from slot 0
+                    const uint32_t id2 = idesc0 + (uint32_t)(n - wrap_at) * idesc_blk;
+                    const uint32_t bo2 = (uint32_t)wrap_at * blk16;
+#pragma unroll
+                    for (int k = 0; k < 3 * NKC; ++k) {
+                      umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
+                      umma_f16_lohi<true>(tmem_base, al[k], bl[k] + bo2, desc_hi, id2);   // (weights end far below 256 KB: no carry out of the address field)
+                    }
                   }
                   umma_commit(empty_bar(stage));   // stage reusable once these MMAs retire
-                  if (i >= 1) { const int t = run_pos + i - 1; umma_commit(tfull_bar(t % NB)); }        // output column i-1 complete
-                  if (i == Lr - 1) { const int t = run_pos + i; umma_commit(tfull_bar(t % NB)); }       // and the run's last one
+                  // this issuer's share of every block of the window; the run's edge blocks have only two
+                  // contributing steps, so the issuer of the edge step stands in for the missing third
+                  if (lo) umma_commit(tfull_bar(s_lo));
+                  umma_commit(tfull_bar(sl));
+                  if (hi_) umma_commit(tfull_bar(s_hi));
+                  if (!lo) mbar_arrive(tfull_bar(sl));
+                  if (!hi_) mbar_arrive(tfull_bar(sl));
+                  stamp(dbg_issue);
                 }
-                __syncwarp();
+                if (++owner == kSwIssuers) owner = 0;
                 if (++stage == p.n_stages) { stage = 0; sphase ^= 1; }
-                if (dbg) { const long long t = clock64(); dbg_issue += t - dbg_t; dbg_t = t; }
+                if (++sl == NB) { sl = 0; pr ^= 1u; }
               }
-              const int t = run_pos + Lr, qd = t / NB;
-              run_pos = t - qd * NB;
-              run_par ^= (uint32_t)(qd & 1);
             }
-          if (leader) umma_commit(layer_bar(cur));   // every MMA of this layer (issued by this warp) has retired
-          __syncwarp();
+          umma_commit(layer_bar(cur));   // every MMA of this layer issued by this warp has retired
         }
       }
-      if (dbg && leader) {
-        p.debug[0] = dbg_w; p.debug[1] = dbg_tempty; p.debug[2] = dbg_full; p.debug[3] = dbg_issue;
-        p.debug[4] = n_my;
+      if constexpr (DBG) {
+        if (dbg) {
+          p.debug[0] = dbg_w; p.debug[1] = dbg_tempty; p.debug[2] = dbg_full; p.debug[3] = dbg_issue;
+          p.debug[4] = n_my; p.debug[5] = dbg_utt; p.debug[6] = dbg_other; p.debug[7] = 0;
+        }
       }
     }
     __syncwarp();
-  } else if (warp >= kSwFrontWarps) {
+  } else {
     // ========================================= epilogue (4*NKC warps) =========================================
     // warp e: TMEM lane quarter q = warp % 4 (rows q*32 .. q*32+31 of the strip), channel group j = e / 4
     // (16 channels = planes 2j, 2j+1).  One block = one output column of one strip.
     const int q = warp & 3;
-    const int j = (warp - kSwFrontWarps) >> 2;
-    const int et = threadIdx.x - 32 * kSwFrontWarps;
+    const int j = warp >> 2;
+    const int et = threadIdx.x;
     int run_pos = 0;
     uint32_t run_par = 0;
     int64_t seq = 0;
+    // cycle accounting of epilogue warp 0 of CTA 0 (HONK2_TC_DEBUG=1)
+    const bool edbg = DBG && p.debug != nullptr && blockIdx.x == 0 && warp == 0;
+    long long e_wait = 0, e_tmem = 0, e_pub = 0, e_math = 0, e_conv0 = 0, e_t = clock64();
     for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
       // ------------------------------ conv_0 -> P (resnet.py:40-44) ------------------------------
       {
@@ -401,112 +470,154 @@ resnet_tc_sweep_kernel(const SwParams p) {
         fence_async_all();   // generic-proxy global writes -> visible to the TMA (async proxy) reads of layer 1
         __syncwarp();
         if (lane == 0) mbar_arrive(conv0_bar);
+        if (edbg) { const long long t = clock64(); e_conv0 += t - e_t; e_t = t; }
       }
 
       for (int l = 0; l < n_layers; ++l, ++seq) {
         const int d = layer_dil(l);
-        const bool has_skip = (l & 1) != 0, last = l == n_layers - 1;
-        const float* kconst = reinterpret_cast<const float*>(p.kconst0 + l * p.layer_stride);
         const int n_runs = d < W ? d : W;
         const int cur = (int)(seq & 1);
-        const uint4* skip_in = bufP + (int64_t)(2 * j) * plane_stride;            // even layers read AND write P
-        uint4* y_out = (has_skip ? bufP : bufQ) + (int64_t)(2 * j) * plane_stride;
-        const uint64_t pol_out = has_skip ? pol_keep : pol_stream;
+        const float* kconst = reinterpret_cast<const float*>(p.kconst0 + l * p.layer_stride);
         float kc_reg[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) kc_reg[c] = __ldg(kconst + 16 * j + c);
-        float psum[16];
+        // The layer body is instantiated per (skip, pooling) variant so that the registers of the skip prefetch
+        // and of the pooled sums are not live together.
+        auto layer_body = [&](auto skip_c, auto last_c) {
+          constexpr bool HAS_SKIP = decltype(skip_c)::value;   // odd l: adds the skip tensor from P, stores to P in place
+          constexpr bool LAST = decltype(last_c)::value;       // pooled instead of stored
+          const uint4* skip_in = bufP + (int64_t)(2 * j) * plane_stride;
+          uint4* y_out = (HAS_SKIP ? bufP : bufQ) + (int64_t)(2 * j) * plane_stride;
+          const uint64_t pol_out = HAS_SKIP ? pol_keep : pol_stream;
+          float psum[LAST ? 16 : 1];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) psum[c] = 0.f;
-        // this layer overwrites the buffer the previous layer READS through TMA: wait until all of its MMAs
-        // (hence all of its loads) have retired before the first store
-        bool guard = l > 0;
-        int pending_w = -1;   // column whose stores still have to be published (one block behind)
-        auto publish = [&](int wcol) {
-          // generic-proxy global stores of this thread -> visible to the async proxy (the TMA loads of the next
-          // layer, issued by this CTA's producer after it acquires the column barrier).  The all-space
-          // fence.proxy.async compiles to MEMBAR.ALL.GPU and, issued by 12 warps per column, stalls the whole
-          // SM; the .global form is a plain view fence.
-          fence_async_global();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(col_bar(cur, wcol));
-        };
-        for (int s = 0; s < n_strips; ++s) {
-          const int row = s * 128 + q * 32 + lane;
-          const bool valid = row < H;
-          for (int r = 0; r < n_runs; ++r) {
-            const int Lr = (W - r + d - 1) / d;
-            for (int o = 0; o < Lr; ++o) {
-              const int w = r + o * d;
-              const int64_t off = (int64_t)w * H + row;
-              uint4 pv[2];
-              if (has_skip && valid) {
+          for (int c = 0; c < (LAST ? 16 : 1); ++c) psum[c] = 0.f;
+          // this layer overwrites the buffer the previous layer READS through TMA: wait until all of its MMAs
+          // (hence all of its loads) have retired before the first store
+          bool guard = l > 0;
+          int pending_w = -1;   // column whose stores still have to be published (one block behind)
+          auto publish = [&](int wcol) {
+            // generic-proxy global stores of this thread -> visible to the async proxy (the TMA loads of the next
+            // layer, issued by this CTA's producer after it acquires the column barrier).  The all-space
+            // fence.proxy.async compiles to MEMBAR.ALL.GPU and, issued by 12 warps per column, stalls the whole
+            // SM; the .global form is a plain view fence.
+            fence_async_global();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(col_bar(cur, wcol));
+          };
+          // block iterator over (strip, run, output column of the run)
+          struct It { int s, r, o, Lr, w; bool done; };
+          auto it_begin = [&]() { It it; it.s = 0; it.r = 0; it.o = 0; it.Lr = (W + d - 1) / d; it.w = 0; it.done = false; return it; };
+          auto it_next = [&](It it) {
+            ++it.o; it.w += d;
+            if (it.o == it.Lr) {
+              it.o = 0;
+              if (++it.r == n_runs) { it.r = 0; if (++it.s == n_strips) it.done = true; }
+              it.w = it.r;
+              it.Lr = (W - it.r + d - 1) / d;
+            }
+            return it;
+          };
+          auto load_skip = [&](uint4 (&pv)[2], const It& it) {
+            if constexpr (HAS_SKIP) {
+              const int row = it.s * 128 + q * 32 + lane;
+              if (!it.done && row < H) {
+                const int64_t off = (int64_t)it.w * H + row;
                 pv[0] = use_pol ? ld_hint(skip_in + off, pol_keep) : skip_in[off];
                 pv[1] = use_pol ? ld_hint(skip_in + off + plane_stride, pol_keep) : skip_in[off + plane_stride];
               }
-              const int t = run_pos + o, qd = t / NB, pos = t - qd * NB;
-              mbar_wait(tfull_bar(pos), run_par ^ (uint32_t)(qd & 1));
-              tc_fence_after();
-              uint32_t v[16];
-              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pos * CP + 16 * j);
-              tmem_ld16(taddr, v);
-              tmem_ld_wait();
-              tmem_st16_zero(taddr);   // the next user of this ring slot accumulates from zero
-              tmem_st_wait();
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(tempty_bar(pos));   // accumulators are in registers, the slot is zero again: free
-              if (pending_w >= 0) { publish(pending_w); pending_w = -1; }
-              if (guard) {
-                mbar_wait(layer_bar(cur ^ 1), (uint32_t)(((seq - 1) >> 1) & 1));
-                guard = false;
-              }
-              if (valid) {
+            }
+          };
+          auto process = [&](const It& it, const uint4 (&pv)[2]) {
+            const int row = it.s * 128 + q * 32 + lane;
+            const bool valid = row < H;
+            const int64_t off = (int64_t)it.w * H + row;
+            const int t = run_pos + it.o, qd = t / NB, pos = t - qd * NB;
+            mbar_wait_sleepy(tfull_bar(pos), run_par ^ (uint32_t)(qd & 1));
+            tc_fence_after();
+            if (edbg) { const long long t = clock64(); e_wait += t - e_t; e_t = t; }
+            uint32_t v[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pos * CP + 16 * j);
+            tmem_ld16(taddr, v);
+            tmem_ld_wait();
+            tmem_st16_zero(taddr);   // the next user of this ring slot accumulates from zero
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(pos));   // accumulators are in registers, the slot is zero again: free
+            if (edbg) { const long long t = clock64(); e_tmem += t - e_t; e_t = t; }
+            if (pending_w >= 0) { publish(pending_w); pending_w = -1; }
+            if (edbg) { const long long t = clock64(); e_pub += t - e_t; e_t = t; }
+            if (guard) {
+              mbar_wait_sleepy(layer_bar(cur ^ 1), (uint32_t)(((seq - 1) >> 1) & 1));
+              guard = false;
+            }
+            if (valid) {
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                  float x[8];
+              for (int hf = 0; hf < 2; ++hf) {
+                float x[8];
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[8 * hf + e]), 0.f) + kc_reg[8 * hf + e];
-                  if (has_skip) {
-                    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[hf]);
+                for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[8 * hf + e]), 0.f) + kc_reg[8 * hf + e];
+                if constexpr (HAS_SKIP) {
+                  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[hf]);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float2 f = __bfloat1622float2(pb[e]);
-                      x[2 * e] += f.x;
-                      x[2 * e + 1] += f.y;
-                    }
-                  }
-                  if (last) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) psum[8 * hf + e] += x[e];
-                  } else {
-                    uint4 yo;
-                    __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-                    if (use_pol) st_hint(y_out + off + hf * plane_stride, yo, pol_out);
-                    else y_out[off + hf * plane_stride] = yo;
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(pb[e]);
+                    x[2 * e] += f.x;
+                    x[2 * e + 1] += f.y;
                   }
                 }
+                if constexpr (LAST) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) psum[8 * hf + e] += x[e];
+                } else {
+                  uint4 yo;
+                  __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+                  if (use_pol) st_hint(y_out + off + hf * plane_stride, yo, pol_out);
+                  else y_out[off + hf * plane_stride] = yo;
+                }
               }
-              pending_w = w;
             }
-            const int t = run_pos + Lr, qd = t / NB;
-            run_pos = t - qd * NB;
-            run_par ^= (uint32_t)(qd & 1);
+            if (edbg) { const long long t = clock64(); e_math += t - e_t; e_t = t; }
+            pending_w = it.w;
+            if (it.o == it.Lr - 1) {   // run finished: advance the ring bookkeeping
+              const int t2 = run_pos + it.Lr, q2 = t2 / NB;
+              run_pos = t2 - q2 * NB;
+              run_par ^= (uint32_t)(q2 & 1);
+            }
+          };
+          // The skip tensor is prefetched two blocks ahead (two register sets, the loop is unrolled by two) so that
+          // its L2 latency hides behind a whole block period.
+          uint4 pa[2], pb2[2];
+          It ia = it_begin(), ib = it_next(ia);
+          load_skip(pa, ia);
+          load_skip(pb2, ib);
+          while (!ia.done) {
+            process(ia, pa);
+            ia = it_next(ib);
+            load_skip(pa, ia);
+            if (ib.done) break;
+            process(ib, pb2);
+            ib = it_next(ia);
+            load_skip(pb2, ib);
           }
-        }
-        if (pending_w >= 0) publish(pending_w);
-        if (last) {
-          // fused global mean (resnet.py:57-58): warp-reduce the 32 rows, one shared atomic per channel
+          if (pending_w >= 0) publish(pending_w);
+          if constexpr (LAST) {
+            // fused global mean (resnet.py:57-58): warp-reduce the 32 rows, one shared atomic per channel
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            float sum = psum[c];
+            for (int c = 0; c < 16; ++c) {
+              float sum = psum[c];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == c) atomicAdd(s_pool + 16 * j + c, sum);
+              for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+              if (lane == c) atomicAdd(s_pool + 16 * j + c, sum);
+            }
           }
-        }
+        };
+        const bool has_skip = (l & 1) != 0, last = l == n_layers - 1;
+        if (has_skip) { if (last) layer_body(std::true_type{}, std::true_type{}); else layer_body(std::true_type{}, std::false_type{}); }
+        else { if (last) layer_body(std::false_type{}, std::true_type{}); else layer_body(std::false_type{}, std::false_type{}); }
       }
 
       // ------------------------------ logits (resnet.py:59) ------------------------------
@@ -523,13 +634,17 @@ resnet_tc_sweep_kernel(const SwParams p) {
       if (et < CP) s_pool[et] = 0.f;
       // the next writers of s_pool (last layer of the next utterance) are at most one accumulator ring
       // ahead of this thread, i.e. far behind this store
+      if (edbg) { const long long t = clock64(); e_math += t - e_t; e_t = t; }
+    }
+    if (edbg && lane == 0) {
+      p.debug[8] = e_wait; p.debug[9] = e_tmem; p.debug[10] = e_pub; p.debug[11] = e_math; p.debug[12] = e_conv0;
     }
   }
 
   // ---- teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kEpiWarps + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

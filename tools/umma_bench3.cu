@@ -71,8 +71,11 @@ __global__ void __launch_bounds__(512, 1) bench3_kernel(const Cfg c, long long* 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_slot;
-  if (warp == 1) {
-    const bool leader = elect_one();
+  const int n_iss = (c.feat & (64 | 256)) ? 3 : 1;
+  const bool by_step = (c.feat & 256) != 0;   // issuer m issues ALL MMAs of steps st % 3 == m
+  if (warp >= 1 && warp <= n_iss) {
+    const int me = warp - 1;
+    const bool leader = (c.feat & 128) ? (lane == 0) : elect_one();
     const uint32_t sbase = smem_u32(smem);
     constexpr uint32_t hi = (128u >> 4) | (1u << 14);
     constexpr uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (8u << 24);
@@ -82,8 +85,10 @@ __global__ void __launch_bounds__(512, 1) bench3_kernel(const Cfg c, long long* 
     const uint32_t a_lbo = ((c.lbo_override ? (uint32_t)c.lbo_override >> 4 : plane16) & 0x3FFFu) << 16;
     const uint32_t kcs = c.kc_stride16 ? (uint32_t)c.kc_stride16 : 2 * plane16;
     constexpr uint32_t b_lbo = ((W_LBO >> 4) & 0x3FFFu) << 16;
-    const uint32_t w16 = (sbase + 1024) >> 4;            // weights: 41.5 KB from +1 KB
-    const uint32_t ring16 = (sbase + 48 * 1024) >> 4;    // 8 stages of 6 planes x box_rows x 16 B from +48 KB
+    // feat 1024: a zero the compiler cannot see through keeps the operands in ordinary registers (R2UR issue path)
+    const uint32_t nz = (c.feat & 1024) ? *reinterpret_cast<volatile uint32_t*>(&bars[31]) >> 31 : 0u;
+    const uint32_t w16 = ((sbase + 1024) >> 4) + nz;            // weights: 41.5 KB from +1 KB
+    const uint32_t ring16 = ((sbase + 48 * 1024) >> 4) + nz;    // 8 stages of 6 planes x box_rows x 16 B from +48 KB
     const uint32_t slot16 = (6 * plane16 * 16 + 127) / 128 * 8;
     int stage = 0, pos = 0;
     const long long t0 = clock64();
@@ -96,14 +101,40 @@ __global__ void __launch_bounds__(512, 1) bench3_kernel(const Cfg c, long long* 
       const uint32_t d1 = tmem + (uint32_t)(((c.feat & 4) || p0 + n <= NB ? p0 : 0) * CP), id1 = idesc0 + (uint32_t)wrap_at * idesc_blk;
       const bool two = wrap_at < n;
       const uint32_t d2 = tmem, bo2 = (uint32_t)wrap_at * blk16, id2 = idesc0 + (uint32_t)(n - wrap_at) * idesc_blk;
-      if (leader) {
+      if (c.feat & 512) {
+        // all operands of the step computed and pinned in registers BEFORE the burst: no register that an
+        // in-flight MMA still reads is rewritten between two MMAs
+        uint32_t al[9], bl[9], bl2[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const int kc = k / 3, dh = k % 3;
+          al[k] = ((a16 + (uint32_t)kc * kcs + (uint32_t)(dh * c.d)) & 0x3FFFu) | a_lbo;
+          const uint32_t b16 = w16 + (uint32_t)((k * W_SLAB) >> 4);
+          bl[k] = (b16 & 0x3FFFu) | b_lbo;
+          bl2[k] = ((b16 + bo2) & 0x3FFFu) | b_lbo;
+          asm volatile("" : "+r"(al[k]), "+r"(bl[k]), "+r"(bl2[k]));
+        }
+        if (leader && (!by_step || st % 3 == me)) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            if (n_iss == 3 && !by_step && k % 3 != me) continue;
+            umma_lohi(d1, al[k], bl[k], hi, id1, 1u);
+            if (two) umma_lohi(d2, al[k], bl2[k], hi, id2, 1u);
+          }
+          if (c.feat & 8) {
+            umma_commit(smem_u32(&bars[stage]));
+            umma_commit(smem_u32(&bars[8 + pos]));
+          }
+        }
+      } else if (leader && (!by_step || st % 3 == me)) {
 #pragma unroll
         for (int kc = 0; kc < 3; ++kc) {
 #pragma unroll
           for (int dh = 0; dh < 3; ++dh) {
+            if (n_iss == 3 && !by_step && dh != me) continue;
             const uint32_t a_lo = ((a16 + (uint32_t)kc * kcs + (uint32_t)(dh * c.d)) & 0x3FFFu) | a_lbo;
             const uint32_t b16 = w16 + (uint32_t)(((kc * 3 + dh) * W_SLAB) >> 4);
-            if (kc == 0 && dh == 0) {
+            if (kc == 0 && dh == 0 && n_iss == 1 && !by_step) {
               int s0 = 0;
               while (s0 < n) {
                 int e = n;
@@ -115,6 +146,8 @@ __global__ void __launch_bounds__(512, 1) bench3_kernel(const Cfg c, long long* 
                           idesc0 + (uint32_t)(e - s0) * idesc_blk, (s0 >= fresh_from || st == 0) ? 0u : 1u);
                 s0 = e;
               }
+            } else if (c.feat & 2048) {
+              umma_lohi(d1, a_lo, (b16 & 0x3FFFu) | b_lbo, hi, id1, 1u);   // no predicated-off twin
             } else {
               umma_lohi(d1, a_lo, (b16 & 0x3FFFu) | b_lbo, hi, id1, 1u);
               if (two) umma_lohi(d2, a_lo, ((b16 + bo2) & 0x3FFFu) | b_lbo, hi, id2, 1u);
@@ -123,18 +156,18 @@ __global__ void __launch_bounds__(512, 1) bench3_kernel(const Cfg c, long long* 
         }
         if (c.feat & 8) {
           umma_commit(smem_u32(&bars[stage]));
-          umma_commit(smem_u32(&bars[8 + pos]));
+          umma_commit(smem_u32(&bars[8 + pos]));   // (barrier counts are 1: phases just flip more often with 3 issuers)
         }
       }
       __syncwarp();
       if (++stage == (c.lbo_override ? 2 : 8)) stage = 0;
       if (++pos == NB) pos = 0;
     }
-    if (leader) umma_commit(smem_u32(&bars[30]));
+    if (leader) umma_commit(smem_u32(&bars[28 + me]));
     __syncwarp();
-    mbar_wait(smem_u32(&bars[30]), 0);
+    mbar_wait(smem_u32(&bars[28 + me]), 0);
     const long long t1 = clock64();
-    if (lane == 0) { cycles[blockIdx.x] = t1 - t0; s_done = 1; }
+    if (lane == 0 && me == 0) { cycles[blockIdx.x] = t1 - t0; s_done = 1; }
   } else if (warp >= 2 && warp < 4 && (c.feat & 16)) {
     // TMA fill emulation: ~13 KB of 16-byte stores per ~650 cycles, into a spare region (+176 KB)
     uint4* dst = reinterpret_cast<uint4*>(smem + 176 * 1024);
@@ -175,8 +208,12 @@ int main() {
   const int ST = 2000;
   printf("%5s %8s %3s | %10s %10s  (ideal 648 cycles per step = 9 x 72)\n", "feat", "box_rows", "d", "cyc/step", "cyc/MMA~");
   struct V { int feat, br, d, lbo, kcs; };
-  const V vs[] = {{0, 136, 1, 0, 0}, {0, 136, 0, 0, 0}, {0, 136, 8, 0, 0}, {0, 136, 1, 65536, 0}, {0, 136, 0, 65536, 0}, {0, 136, 0, 65536, 256},
-                  {0, 136, 0, 4096, 0}, {0, 136, 0, 8192, 0}, {0, 136, 0, 16384, 0}, {0, 128, 0, 0, 0}, {0, 256, 0, 0, 0}};
+  const V vs[] = {{2048, 136, 1, 0, 0}, {2048 + 1, 136, 1, 0, 0}, {2048 + 1 + 8, 136, 1, 0, 0}, {2048 + 128, 136, 1, 0, 0}, {2048 + 256 + 1 + 8, 136, 1, 0, 0}, {2048 + 64 + 1 + 8, 136, 1, 0, 0},
+                  {1024 + 128, 136, 1, 0, 0}, {1024 + 128 + 64, 136, 1, 0, 0}, {1024 + 128 + 64 + 1 + 4, 136, 1, 0, 0}, {1024 + 128 + 64 + 1 + 4 + 8, 136, 1, 0, 0},
+                  {1024 + 128 + 256, 136, 1, 0, 0}, {1024 + 128 + 256 + 1 + 4 + 8, 136, 1, 0, 0}, {128 + 64, 136, 1, 0, 0}, {64, 136, 1, 0, 0},
+                  {0, 136, 1, 0, 0}, {512, 136, 1, 0, 0}, {512 + 1, 136, 1, 0, 0}, {512 + 1 + 4, 136, 1, 0, 0}, {512 + 1 + 4 + 8, 136, 1, 0, 0},
+                  {512 + 64 + 1 + 4 + 8, 136, 1, 0, 0}, {512 + 256 + 1 + 4 + 8, 136, 1, 0, 0},
+                  {512 + 1 + 4 + 8 + 16 + 32, 136, 1, 0, 0}, {512 + 256 + 1 + 4 + 8 + 16 + 32, 160, 16, 0, 0}};
   for (const V& v : vs) {
       const int feat = v.feat, br = v.br;
       Cfg c{feat, ST, br, v.d, v.lbo, v.kcs};
