@@ -41,6 +41,21 @@ FLOPS_PER_UTT = {  # SURVEY.md section 8d / BASELINE.md section 3 (2*MAC, padded
 }
 
 
+def committed_traffic(kernel_path, batch):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same command
+    (profiles/*traffic*.json; the newest record whose kernel and batch match), or None."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*traffic*.json"))):
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
+        if kernel_path in d.get("kernel", "") and d.get("batch_per_launch") == batch:
+            best = d
+    return None if best is None else {"dram_bytes_per_launch": best["dram_bytes_per_launch"], "source": best.get("source")}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -290,8 +305,12 @@ def main():
         avg_s = prof["conv_ms"] / prof["conv_launches"] / 1e3
         achieved = flops_per_launch / avg_s / 1e12
         peak = pk["bf16_tflops_sustained"]
+        tr = committed_traffic(prof.get("kernel_path", "?"), B)
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": prof["conv_kernel"], "launches": prof["conv_launches"],
+                "traffic": None if tr is None else tr["dram_bytes_per_launch"],
+                "traffic_source": None if tr is None else tr["source"],
+                "frac_of_burst_peak": achieved / pk["bf16_tflops"],
+                "kernel": prof["conv_kernel"], "launches": prof["conv_launches"],
                 "avg_launch_ms": prof["conv_ms"] / prof["conv_launches"], "peak_source": pk["source"] + " (sustained bf16)",
                 "share_of_step": prof["conv_ms"] / max(prof["total_ms"], 1e-9),
                 "frontend_ms_per_step": prof["frontend_ms"] / K, "other_ms_per_step": prof["other_ms"] / K}

@@ -1476,6 +1476,16 @@ size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int
   return need;
 }
 
+const char* tc_resnet_kernel_path(const TcResNet* p, int T, int F) {
+  if (!p || !p->supported) return "unsupported";
+  int H, W;
+  tc_map_hw(p->cfg, T, F, &H, &W);
+  if (H < 1 || W < 1 || W > 256 || !tc_layers_ok(p, H, W)) return "unsupported";
+  if (tc_sweep_plan(p, H, W).ok) return "resnet_tc_sweep_kernel";
+  if (tc_fused_plan(p, H, W).ok) return "resnet_tc_fused_kernel";
+  return "conv3x3_tc_kernel";
+}
+
 template <int NKC, bool HAS_PREV, bool DO_POOL>
 static int tc_launch_conv3(const CUtensorMap& map, const TcConvParams& prm, int grid, cudaStream_t st) {
   KWS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NKC, HAS_PREV, DO_POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize,

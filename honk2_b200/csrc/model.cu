@@ -538,6 +538,12 @@ extern "C" int kws_model_forward_wave(kws_model_t* m, const kws_frontend_t* fe, 
 
 extern "C" int64_t kws_model_last_launches(const kws_model_t* m) { return m ? m->last_launches : 0; }
 
+extern "C" const char* kws_model_kernel_path(const kws_model_t* m, int T, int F, int precision) {
+  if (m == nullptr) return "unsupported";
+  if (precision != KWS_BF16) return "fp32 CUDA-core kernels";
+  return m->tc != nullptr ? tc_resnet_kernel_path(m->tc, T, F) : "unsupported";
+}
+
 extern "C" int kws_model_set_profile(kws_model_t* m, int enabled) {
   KWS_REQUIRE(m != nullptr, "kws_model_set_profile: model is null");
   m->prof.enabled = enabled != 0;

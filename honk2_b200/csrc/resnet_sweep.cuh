@@ -262,8 +262,14 @@ resnet_tc_sweep_kernel(const SwParams p) {
     // and every issuer waits for the ring slot of every block of its window to be drained, not only the fresh one,
     // because nothing orders the issuers among themselves.
     const int me = warp - kEpiWarps - 1;
-    const uint32_t nz = p.issue_style ? *reinterpret_cast<volatile uint32_t*>(smem + kSwZero) : 0u;
-    if (lane == 0 && n_seq > 0) {
+    // Whole warp walks the schedule with warp-uniform values only (kernel parameters, counters, the TMEM base
+    // broadcast by a shuffle), so the descriptors live in uniform registers and an MMA costs 2-3 instructions
+    // instead of the 17-instruction ELECT / R2UR / branch sequence the compiler emits for per-thread operands;
+    // one elected lane issues the MMAs, commits and arrivals.
+    const bool leader = elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    constexpr uint32_t nz = 0u;
+    if (n_seq > 0) {
       int stage = 0;
       uint32_t sphase = 0;
       int owner = 0;            // issuer of the current step (global step counter mod 3)
@@ -317,7 +323,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   // All operands of the step are computed BEFORE the burst, and the burst is straight-line code
                   // without predicated-off MMAs (separate path for the wrapped window).
                   const uint32_t a16 = ((sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes) >> 4) + row0 + nz;
-                  const uint32_t d1 = tmem_base + (uint32_t)(p0 * CP);
+                  const uint32_t d1 = tmem_u + (uint32_t)(p0 * CP);
                   const uint32_t id1 = idesc0 + (uint32_t)wrap_at * idesc_blk;
                   uint32_t al[3 * NKC], bl[3 * NKC];
 #pragma unroll
@@ -327,7 +333,9 @@ resnet_tc_sweep_kernel(const SwParams p) {
                       al[kc * 3 + dh] = ((a16 + (uint32_t)(2 * kc) * plane16 + (uint32_t)(dh * d)) & 0x3FFFu) | a_lbo;
                       bl[kc * 3 + dh] = ((w16 + (uint32_t)(((kc * 3 + dh) * W_SLAB) >> 4) + (uint32_t)blk0 * blk16) & 0x3FFFu) | b_lbo;
                     }
-                  if (wrap_at == n) {
+                  if (!leader) {
+                    // (only the elected lane issues)
+                  } else if (wrap_at == n) {
 #pragma unroll
                     for (int k = 0; k < 3 * NKC; ++k) umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
                   } else {
@@ -337,9 +345,10 @@ resnet_tc_sweep_kernel(const SwParams p) {
 #pragma unroll
                     for (int k = 0; k < 3 * NKC; ++k) {
                       umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
-                      umma_f16_lohi<true>(tmem_base, al[k], bl[k] + bo2, desc_hi, id2);   // (weights end far below 256 KB: no carry out of the address field)
+                      umma_f16_lohi<true>(tmem_u, al[k], bl[k] + bo2, desc_hi, id2);   // (weights end far below 256 KB: no carry out of the address field)
                     }
                   }
+                  if (leader) {
                   umma_commit(empty_bar(stage));   // stage reusable once these MMAs retire
                   // this issuer's share of every block of the window; the run's edge blocks have only two
                   // contributing steps, so the issuer of the edge step stands in for the missing third
@@ -348,6 +357,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   if (hi_) umma_commit(tfull_bar(s_hi));
                   if (!lo) mbar_arrive(tfull_bar(sl));
                   if (!hi_) mbar_arrive(tfull_bar(sl));
+                  }
+                  __syncwarp();
                   stamp(dbg_issue);
                 }
                 if (++owner == kSwIssuers) owner = 0;
@@ -355,11 +366,12 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 if (++sl == NB) { sl = 0; pr ^= 1u; }
               }
             }
-          umma_commit(layer_bar(cur));   // every MMA of this layer issued by this warp has retired
+          if (leader) umma_commit(layer_bar(cur));   // every MMA of this layer issued by this warp has retired
+          __syncwarp();
         }
       }
       if constexpr (DBG) {
-        if (dbg) {
+        if (dbg && leader) {
           p.debug[0] = dbg_w; p.debug[1] = dbg_tempty; p.debug[2] = dbg_full; p.debug[3] = dbg_issue;
           p.debug[4] = n_my; p.debug[5] = dbg_utt; p.debug[6] = dbg_other; p.debug[7] = 0;
         }

@@ -59,10 +59,14 @@ def profile_layers(model, audio_processor, wave_sets, steps):
     finally:
         lib.kws_model_set_profile(st["handle"], 0)
     launches = int(conv_n.value)
-    if launches == steps and kernel.startswith("conv3x3"):
-        kernel = ("resnet_tc_fused_kernel: conv_0 + %d x (conv3x3 + ReLU + skip + BN) + mean + Linear in ONE launch "
-                  "(FLOPs counted: the C->C convolutions)" % model.n_layers)
+    path = lib.kws_model_kernel_path(st["handle"], T, audio_processor.n_mels, model._precision_id())
+    path = path.decode() if path else "unknown"
+    if launches == steps and kernel.startswith("conv3x3") and path in ("resnet_tc_sweep_kernel", "resnet_tc_fused_kernel"):
+        kernel = ("%s: conv_0 + %d x (conv3x3 + ReLU + skip + BN) + mean + Linear in ONE launch "
+                  "(FLOPs counted: the C->C convolutions)" % (path, model.n_layers))
+    else:
+        kernel = "%s: %s" % (path, kernel)
     return {"conv_ms": conv_ms.value, "conv_launches": launches, "other_ms": other_ms.value,
             "other_launches": int(other_n.value), "frontend_ms": fe_ms,
             "total_ms": conv_ms.value + other_ms.value + fe_ms,
-            "conv_flops_per_launch": per_utt * B * steps / max(launches, 1), "conv_kernel": kernel}
+            "conv_flops_per_launch": per_utt * B * steps / max(launches, 1), "conv_kernel": kernel, "kernel_path": path}

@@ -126,6 +126,10 @@ int kws_model_forward_wave(kws_model_t* m, const kws_frontend_t* fe, const float
                            size_t workspace_bytes, void* stream);
 /* Number of kernel launches the last forward on this handle issued (bench "gpu_launches"). */
 int64_t kws_model_last_launches(const kws_model_t* m);
+/* Name of the kernel family a forward of a [B][T][F] batch runs in the given precision (bench / profile labels):
+ * "resnet_tc_sweep_kernel", "resnet_tc_fused_kernel", "conv3x3_tc_kernel", "fp32 CUDA-core kernels" or
+ * "unsupported".  Static string, never freed. */
+const char* kws_model_kernel_path(const kws_model_t* m, int T, int F, int precision);
 /* Per-launch timing for the bench roofline: while enabled, kws_model_forward brackets every
  * layer launch with CUDA events and synchronises the stream before returning.
  * kws_model_profile_read returns (and clears) the accumulated milliseconds / launch counts of

@@ -299,3 +299,32 @@ def test_bf16_not_available_for_cnn(dev):
     m, _ = gpu_model("cnn-trad-fpool3", "default", dev, precision="bf16")
     with pytest.raises(honk2_b200.NativeError):
         m(torch.zeros(2, 101, 40, device=dev))
+
+
+def test_bf16_column_sweep_kernel_matches_position_major_kernel_at_full_batch(dev, monkeypatch):
+    """BASELINE size (8192 x 1 s): the two whole-network tensor-core kernels (column sweep, resnet_sweep.cuh;
+    position major, resnet_fused.cuh) compute the same network from the same bf16 operands and differ only in the
+    order of the fp32 accumulation.  Any stale column (a missed cross-proxy fence between the epilogue's stores and
+    the next layer's bulk copies) or lost accumulator update would show up as a gross per-utterance error; repeated
+    launches also have to agree with each other."""
+    ap = AudioProcessor()
+    w = torch.from_numpy(synth.broadband(8192, seed=11)).to(dev)
+    with torch.no_grad():
+        feats = ap.compute_mfccs_batch(w)
+        monkeypatch.setenv("HONK2_TC_SWEEP", "1")
+        m_sweep, sd = gpu_model("res15", "hardened", dev, precision="bf16")
+        ys = [m_sweep(feats) for _ in range(3)]
+        monkeypatch.setenv("HONK2_TC_SWEEP", "0")
+        m_pos, _ = gpu_model("res15", "hardened", dev, precision="bf16")
+        y_pos = m_pos(feats)
+    scale = float(y_pos.abs().max())
+    assert torch.isfinite(ys[0]).all()
+    for y in ys:
+        assert float((y - y_pos).abs().max()) <= 1e-2 * scale
+    assert float((ys[0] - ys[1]).abs().max()) <= 2e-3 * scale
+    assert float((ys[0] - ys[2]).abs().max()) <= 2e-3 * scale
+    # sampled rows against the fp32 CPU oracle
+    kind, cfg = model_config("res15")
+    idx = np.random.default_rng(2).choice(8192, 8, replace=False)
+    ref = model_ref.forward(kind, sd, cfg, feats[torch.from_numpy(idx).to(dev)].cpu()).numpy()
+    assert logit_err(ys[0][torch.from_numpy(idx).to(dev)].cpu().numpy(), ref) <= BF16_TOL
