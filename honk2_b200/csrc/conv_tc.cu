@@ -807,6 +807,24 @@ __global__ void pack_conv3x3_sw_kernel(const float* __restrict__ w, const float*
   }
 }
 
+// conv_0 weights [C][1][3][3] fp32 -> one-chunk sweep slab set [3 dh][2 K halves][3 blocks][CP][8] bf16: the staged
+// "activation" of the conv_0 pseudo-layer carries the bf16 high and low parts of the feature in channels 0 and 1, so
+// the weight sits in both positions (k = 0, 1 of K half 0) and everything else is zero.
+__global__ void pack_conv0_sw_kernel(const float* __restrict__ w0, __nv_bfloat16* __restrict__ out, int C, int CP) {
+  const int total = 3 * 2 * 3 * CP * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 7;
+    int t = i >> 3;
+    const int co = t % CP; t /= CP;
+    const int blk = t % 3; t /= 3;
+    const int half = t & 1; t >>= 1;
+    const int dh = t;
+    const int tap = dh * 3 + (2 - blk);
+    const float v = (half == 0 && e < 2 && co < C) ? w0[co * 9 + tap] : 0.f;
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // Per-layer epilogue constants.  The activation stored by layer i is z_i = x_i - mean_i (the 1/sigma
 // factor is folded into layer i+1's weights).  The skip tensor x_{i-2} of an even layer is not stored:
 // it is z_{i-2} + mean_{i-2}, so z_i = ReLU(conv) + z_{i-2} + (mean_{i-2} - mean_i)   (resnet.py:49-55).
@@ -860,6 +878,7 @@ struct TcResNet {
   std::vector<__nv_bfloat16*> wpack_sw;     // per layer, column-sweep layout (resnet_sweep.cuh)
   std::vector<float*> scale_p, shift_p;     // per layer, padded to CP: BN 1/sigma and the epilogue constant
   float* conv0_w = nullptr;                 // [C][9]
+  __nv_bfloat16* conv0_wb = nullptr;        // conv_0 as a one-chunk sweep slab set (pack_conv0_sw_kernel)
   float* out_w = nullptr;
   float* out_b = nullptr;
   std::map<std::tuple<const void*, int64_t, int, int, int>, CUtensorMap> maps;
@@ -1004,7 +1023,8 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
     const int n = cfg.n_layers;
     const size_t w_bytes = round_up<size_t>((size_t)9 * p->NKC * 2 * p->CP * 16, 256);
     const size_t v_bytes = round_up<size_t>(p->CP * sizeof(float), 256);
-    const size_t total = n * (2 * w_bytes + 2 * v_bytes) + round_up<size_t>(C * 9 * 4, 256) +
+    const size_t c0_bytes = round_up<size_t>((size_t)3 * 2 * 3 * p->CP * 16, 256);
+    const size_t total = n * (2 * w_bytes + 2 * v_bytes) + c0_bytes + round_up<size_t>(C * 9 * 4, 256) +
                          round_up<size_t>((size_t)cfg.n_labels * C * 4, 256) + round_up<size_t>(cfg.n_labels * 4, 256);
     if (cudaMalloc(&p->blob, total) != cudaSuccess) {
       set_error("tc_resnet_create: cudaMalloc(%zu) failed", total);
@@ -1018,6 +1038,7 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
       p->scale_p.push_back(reinterpret_cast<float*>(b)); b += v_bytes;
       p->shift_p.push_back(reinterpret_cast<float*>(b)); b += v_bytes;
     }
+    p->conv0_wb = reinterpret_cast<__nv_bfloat16*>(b); b += c0_bytes;
     p->conv0_w = reinterpret_cast<float*>(b); b += round_up<size_t>(C * 9 * 4, 256);
     p->out_w = reinterpret_cast<float*>(b); b += round_up<size_t>((size_t)cfg.n_labels * C * 4, 256);
     p->out_b = reinterpret_cast<float*>(b);
@@ -1071,6 +1092,8 @@ int tc_resnet_set_weights(TcResNet* p, const kws_resnet_weights& w, float* const
     KWS_CUDA(cudaGetLastError());
   }
   KWS_CUDA(cudaMemcpyAsync(p->conv0_w, w.conv0_w, sizeof(float) * C * 9, cudaMemcpyDeviceToDevice, st));
+  pack_conv0_sw_kernel<<<ceil_div(3 * 2 * 3 * p->CP * 8, 256), 256, 0, st>>>(w.conv0_w, p->conv0_wb, C, p->CP);
+  KWS_CUDA(cudaGetLastError());
   KWS_CUDA(cudaMemcpyAsync(p->out_w, w.out_w, sizeof(float) * L * C, cudaMemcpyDeviceToDevice, st));
   KWS_CUDA(cudaMemcpyAsync(p->out_b, w.out_b, sizeof(float) * L, cudaMemcpyDeviceToDevice, st));
   return KWS_OK;
@@ -1297,7 +1320,7 @@ static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat
 struct TcSweepPlan {
   bool ok = false;
   int n_slots = 0, n_strips = 0, smem_total = 0, n_stages = 0;
-  int w_off[2] = {0, 0}, ring_off = 0, slot_bytes = 0;
+  int c0w_off = 0, w_off[2] = {0, 0}, ring_off = 0, slot_bytes = 0;
   std::vector<int> dil;
 };
 
@@ -1306,6 +1329,7 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W) {
   const kws_resnet_config& c = p->cfg;
   if (!p->sweep_enabled || c.n_layers < 1 || c.n_layers > kFusedMaxLayers || c.n_labels > 4096) return f;
   if (W < 1 || W > kSwMaxW || H < 1) return f;
+  if (c.pool_h > 1 || c.pool_w > 1) return f;   // conv_0 runs as a tensor-core pseudo-layer on the unpooled map
   f.n_strips = ceil_div(H, 128);
   // the 128 lanes of an MMA are 128 rows of one column: short maps (res8 / res26 after pooling) would leave
   // most lanes idle and stay on the position-major kernel
@@ -1320,7 +1344,8 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W) {
   }
   f.n_slots = p->n_sms;
   const int w_bytes = 9 * p->NKC * 2 * p->CP * 16;
-  f.w_off[0] = kSwCtrlBytes;
+  f.c0w_off = kSwCtrlBytes;
+  f.w_off[0] = f.c0w_off + round_up(3 * 2 * 3 * p->CP * 16, 128);
   f.w_off[1] = f.w_off[0] + round_up(w_bytes, 128);
   f.ring_off = round_up(f.w_off[1] + w_bytes, 1024);
   f.slot_bytes = round_up(p->NP * ((128 + 2 * dmax + 7) & ~7) * 16, 128);
@@ -1394,14 +1419,15 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
     q.kconst0 = reinterpret_cast<const unsigned char*>(p->shift_p[0]);
     q.layer_stride = n > 1 ? (int64_t)(reinterpret_cast<const unsigned char*>(p->wpack_sw[1]) - q.wpack0) : 0;
     q.use_dilation = c.use_dilation ? 1 : 0;
-    q.conv0_w = p->conv0_w;
+    q.conv0_wb = reinterpret_cast<const unsigned char*>(p->conv0_wb);
     q.last_scale = p->scale_p[n - 1];
     q.out_w = p->out_w;
     q.out_b = p->out_b;
     q.P = P; q.Q = Q;
     q.n_layers = n; q.C = c.n_maps; q.n_labels = c.n_labels; q.T = T; q.F = F;
-    q.ph = c.pool_h > 0 ? c.pool_h : 1; q.pw = c.pool_w > 0 ? c.pool_w : 1;
+    q.ph = 1; q.pw = 1;
     q.H = H; q.W = W; q.n_strips = f.n_strips;
+    q.smem_c0w_off = f.c0w_off;
     {
       static const bool bulk_on = [] { const char* e = std::getenv("HONK2_TC_SWEEP_BULK"); return e == nullptr || std::atoi(e) != 0; }();
       int dmax = 1;
@@ -1441,6 +1467,11 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
       long long h[16];
       cudaStreamSynchronize(st);
       cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+      const double ptot = (double)(h[13] + h[14] + h[15] + h[7]);
+      fprintf(stderr, "[sweep dbg] producer of CTA 0: waiting for the previous layer's column %.1f%%, for a free stage %.1f%%, building "
+              "conv_0 columns %.1f%%, issuing copies / weights / bookkeeping %.1f%% (total %.0f)\n",
+              100 * h[13] / ptot, 100 * h[14] / ptot, 100 * h[15] / ptot, 100 * h[7] / ptot, ptot);
+      h[7] = 0;
       const double tot = (double)(h[0] + h[1] + h[2] + h[3] + h[5] + h[6] + h[7]);
       fprintf(stderr, "[sweep dbg] issuer 0 of CTA 0, %lld utterances, cycles: weights wait %.1f%%, accumulator-free wait %.1f%%, "
               "TMA-data wait %.1f%%, utterance boundary (tail + conv_0 + first load) %.1f%%, issuing own steps %.1f%%, first loop top after an own step %.1f%%, counting along %.1f%% "

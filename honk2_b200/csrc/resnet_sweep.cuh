@@ -22,6 +22,12 @@
 // is exactly the reference's zero padding (resnet.py:22-24, padding = dilation).  The +-d row shift
 // of a height tap is a descriptor start-address offset.
 //
+// conv_0 (1 -> C, resnet.py:18) runs in the same pipeline as a pseudo-layer with ONE 16-channel chunk whose only
+// live "channels" are the bf16 high and low parts of the fp32 feature (the weight slab holds w in both positions, so
+// the product is fp32-feature x bf16-weight): the producer warp writes the staged column itself instead of copying
+// it, three N = 3*CP MMAs per column do the rest, and the ordinary epilogue applies ReLU and stores.  There is no
+// CUDA-core convolution and no pipeline drain between utterances.
+//
 // There is no CTA-wide barrier between layers.  Dependencies are tracked per map column with
 // mbarriers: the producer loads column w of layer l+1 as soon as the epilogue has stored column w of
 // layer l (col_done), the epilogue of layer l+1 starts storing only after every MMA of layer l has
@@ -71,7 +77,7 @@ struct SwParams {
   const CUtensorMap* maps;      // [n_layers]  input tensor map of every layer (global memory, 64 B aligned)
   int use_dilation;
   const float* feat;            // [B][T][F]
-  const float* conv0_w;         // [C][9]
+  const unsigned char* conv0_wb; // conv_0 weights as a one-chunk sweep slab set: [3 dh][2 K halves][3 blocks][CP][8] bf16
   const float* last_scale;      // [CP]
   const float* out_w;           // [n_labels][C]
   const float* out_b;           // [n_labels]
@@ -81,6 +87,7 @@ struct SwParams {
   int64_t B;
   int n_layers, C, n_labels, T, F, ph, pw, H, W;
   int n_strips;                 // ceil(H / 128)
+  int smem_c0w_off;             // conv_0 weight slabs (3 * 2 * 3*CP*16 bytes), resident for the whole kernel
   int smem_w_off[2], smem_ring_off, ring_slot_bytes, n_stages;
   int l2_policy;
   int bulk_rows;                // > 0 (single-strip maps): columns are staged with 1-D bulk copies of bulk_rows = H rows per plane
@@ -111,33 +118,33 @@ resnet_tc_sweep_kernel(const SwParams p) {
   auto tempty_bar = [&](int a) { return sbase + kSwBarTempty + 8u * a; };
   auto wfull_bar = [&](int i) { return sbase + kSwBarWfull + 8u * i; };
   auto layer_bar = [&](int i) { return sbase + kSwBarLayer + 8u * i; };
-  const uint32_t conv0_bar = sbase + kSwBarConv0;
   auto col_bar = [&](int par, int w) { return sbase + kSwBarCol + 8u * (par * kSwMaxW + w); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSwTmemSlot);
   float* s_pool = reinterpret_cast<float*>(smem + kSwPool);
-  float* s_w0 = reinterpret_cast<float*>(smem + kSwW0);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int n_layers = p.n_layers, H = p.H, W = p.W, n_strips = p.n_strips;
   const int64_t n_my = (p.B - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const int64_t n_seq = n_my * n_layers;
+  const int64_t n_wq = n_my * n_layers;        // real (C -> C) layers this CTA runs
+  const int64_t n_seq = n_wq;
+  const int nl1 = n_layers + 1;                 // pseudo-layers per utterance: conv_0, then the C -> C layers
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NB; ++a) { mbar_init(tfull_bar(a), kSwIssuers); mbar_init(tempty_bar(a), kEpiWarps); }
     for (int i = 0; i < 2; ++i) { mbar_init(wfull_bar(i), 1); mbar_init(layer_bar(i), kSwIssuers); }
-    mbar_init(conv0_bar, kEpiWarps);
     for (int par = 0; par < 2; ++par)
       for (int w = 0; w < W; ++w) mbar_init(col_bar(par, w), (uint32_t)(kEpiWarps * n_strips));
     fence_barrier_init();
   }
   if (threadIdx.x == 32) *reinterpret_cast<volatile uint32_t*>(smem + kSwZero) = 0u;
   if (warp == kEpiWarps + 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  for (int i = threadIdx.x; i < CP * 12; i += sw_threads(NKC)) {
-    const int c = i / 12, k = i - c * 12;
-    s_w0[i] = (k < 9 && c < p.C) ? p.conv0_w[c * 9 + k] : 0.f;
+  {   // conv_0 weight slabs -> shared memory (generic copy; the fence below publishes it to the tensor core)
+    const uint4* src = reinterpret_cast<const uint4*>(p.conv0_wb);
+    uint4* dst = reinterpret_cast<uint4*>(smem + p.smem_c0w_off);
+    for (int i = threadIdx.x; i < (3 * W_SLAB) / 16; i += sw_threads(NKC)) dst[i] = src[i];
   }
   for (int i = threadIdx.x; i < CP; i += sw_threads(NKC)) s_pool[i] = 0.f;
   if (p.bulk_rows > 0) {
@@ -145,8 +152,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
     uint4* ring = reinterpret_cast<uint4*>(smem + p.smem_ring_off);
     const int n16 = p.n_stages * (p.ring_slot_bytes >> 4);
     for (int i = threadIdx.x; i < n16; i += sw_threads(NKC)) ring[i] = make_uint4(0u, 0u, 0u, 0u);
-    fence_async_smem();   // generic-proxy zeros -> visible to the tensor core's (async proxy) operand reads
   }
+  fence_async_smem();   // generic-proxy writes (zeros, conv_0 weights) -> visible to the tensor core's (async proxy) reads
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -183,51 +190,109 @@ resnet_tc_sweep_kernel(const SwParams p) {
     if (n_seq > 0) {
       int stage = 0;
       uint32_t sphase = 0;
-      int64_t seq = 0, utt = 0;
+      int64_t sq = 0;      // pseudo-layer counter (conv_0 included): parity of the layer / column barriers
+      int64_t wq = 0;      // real-layer counter: parity of the weight buffers
+      const bool pdbg = DBG && p.debug != nullptr && blockIdx.x == 0;
+      long long pd_col = 0, pd_empty = 0, pd_c0 = 0, pd_issue = 0, pd_t = DBG ? clock64() : 0;
+      auto pstamp = [&](long long& bucket) {
+        if constexpr (DBG) { if (pdbg) { const long long t = clock64(); bucket += t - pd_t; pd_t = t; } }
+      };
       if (leader) {
         mbar_expect_tx(wfull_bar(0), W_BYTES);
         bulk_load(sbase + p.smem_w_off[0], p.wpack0, W_BYTES, wfull_bar(0));
       }
-      for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x, ++utt) {
-        for (int l = 0; l < n_layers; ++l, ++seq) {
-          const CUtensorMap* map = p.maps + l;
-          const int d = layer_dil(l), box_rows = box_rows_of(d);
+      for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+        const float* feat_b = p.feat + b * (int64_t)p.T * p.F;
+        float4 c0_f[5];   // conv_0: this lane's rows of the current group of four feature columns
+        const bool c0_vec = (p.F & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feat) & 15) == 0;
+        for (int ll = 0; ll < nl1; ++ll, ++sq) {
+          const bool is_c0 = ll == 0;
+          const int l = ll - 1;
+          const CUtensorMap* map = p.maps + (is_c0 ? 0 : l);
+          const int d = is_c0 ? 1 : layer_dil(l), box_rows = box_rows_of(d);
           const int n_runs = d < W ? d : W;
           const uint32_t tx = (uint32_t)(NP * box_rows * 16);
-          const bool in_q = (l & 1) != 0;
+          const bool in_q = !is_c0 && (l & 1) != 0;
           const uint64_t pol = in_q ? pol_stream : pol_keep;
-          bool w_pending = seq + 1 < n_seq;
+          bool w_pending = !is_c0 && wq + 1 < n_wq;
           auto request_weights = [&]() {
-            // buffer (seq+1)&1 was read by the MMAs of layer seq-1: wait until they have retired
-            if (seq >= 1) mbar_wait(layer_bar((int)((seq - 1) & 1)), (uint32_t)(((seq - 1) >> 1) & 1));
+            // buffer (wq+1)&1 was read by the MMAs of the previous real layer: wait until they have retired
+            // (that layer is the previous pseudo-layer, or the one before conv_0 when this is the utterance's first)
+            if (wq >= 1) {
+              const int64_t sp = l >= 1 ? sq - 1 : sq - 2;
+              mbar_wait(layer_bar((int)(sp & 1)), (uint32_t)((sp >> 1) & 1));
+            }
             const int nl = (l + 1 < n_layers) ? l + 1 : 0;
-            const int nb = (int)((seq + 1) & 1);
+            const int nb = (int)((wq + 1) & 1);
             if (leader) {
               mbar_expect_tx(wfull_bar(nb), W_BYTES);
               bulk_load(sbase + p.smem_w_off[nb], p.wpack0 + nl * p.layer_stride, W_BYTES, wfull_bar(nb));
             }
             w_pending = false;
           };
-          if (l == 0) mbar_wait(conv0_bar, (uint32_t)(utt & 1));   // conv_0 of this utterance is in P
-          const int prev_par = (int)((seq - 1) & 1);
-          const uint32_t prev_phase = (uint32_t)(((seq - 1) >> 1) & 1);
+          const int prev_par = (int)((sq - 1) & 1);
+          const uint32_t prev_phase = (uint32_t)(((sq - 1) >> 1) & 1);
           int step = 0;
           for (int s = 0; s < n_strips; ++s)
             for (int r = 0; r < n_runs; ++r)
               for (int w = r; w < W; w += d, ++step) {
                 if (w_pending && step == kSwWeightStep) request_weights();
-                if (l > 0) mbar_wait(col_bar(prev_par, w), prev_phase);   // column w of the previous layer is stored
-                mbar_wait(empty_bar(stage), sphase ^ 1);
+                pstamp(pd_issue);
+                if (!is_c0) mbar_wait_lean(col_bar(prev_par, w), prev_phase);   // column w of the previous pseudo-layer is stored
+                pstamp(pd_col);
+                mbar_wait_lean(empty_bar(stage), sphase ^ 1);
+                pstamp(pd_empty);
                 const uint32_t dst = sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes;
-                if (p.bulk_rows > 0) {
+                if (is_c0) {
+                  // conv_0 column: rows 128 s - 1 .. 128 s + 128 of feature column w, each as {hi, lo, 0 x 6} bf16 in
+                  // plane 0 and zeros in plane 1 (written, not assumed: whatever an earlier layer left there must not
+                  // reach this utterance, 0 x NaN = NaN); zero outside the map = the reference's padding
+                  unsigned char* slot = smem + p.smem_ring_off + (size_t)stage * p.ring_slot_bytes;
+                  const int r0 = row0_of(1);
+                  // the features of four consecutive columns are fetched together (one 16-byte load per row), so only
+                  // every fourth column pays the L2 latency
+                  if ((w & 3) == 0 || !c0_vec) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                      const int h = s * 128 - 1 + lane + 32 * k;
+                      const bool ok = lane + 32 * k < 130 && h >= 0 && h < p.T;
+                      if (c0_vec) {
+                        c0_f[k] = ok ? __ldg(reinterpret_cast<const float4*>(feat_b + (int64_t)h * p.F + w)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                      } else {
+                        c0_f[k].x = ok ? __ldg(feat_b + (int64_t)h * p.F + w) : 0.f;
+                      }
+                    }
+                  }
+#pragma unroll
+                  for (int k = 0; k < 5; ++k) {
+                    const int rr = lane + 32 * k;
+                    if (rr < 130) {
+                      const int c = c0_vec ? (w & 3) : 0;
+                      const float v = c == 0 ? c0_f[k].x : (c == 1 ? c0_f[k].y : (c == 2 ? c0_f[k].z : c0_f[k].w));
+                      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+                      const uint32_t packed = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+                      *reinterpret_cast<uint4*>(slot + (size_t)(r0 + rr) * 16) = make_uint4(packed, 0u, 0u, 0u);
+                      *reinterpret_cast<uint4*>(slot + (size_t)(box_rows + r0 + rr) * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                  }
+                  fence_async_smem();   // generic-proxy writes -> visible to the tensor core
+                  __syncwarp();
+                  if (leader) mbar_arrive(full_bar(stage));
+                  pstamp(pd_c0);
+                } else if (p.bulk_rows > 0) {
                   // one contiguous H x 16 B run per 8-channel plane (a TMA box with 16-byte rows fetches a whole
                   // 32-byte sector per row: 2.6x the bytes, measured with ncu)
+                  // (issued by ONE lane with warp-uniform operands: per-lane operands would make the compiler wrap every
+                  // copy in a 15-instruction ELECT / R2UR loop, and this warp's instruction count is what bounds it)
                   const uint32_t bytes = (uint32_t)p.bulk_rows * 16u;
-                  if (leader) mbar_expect_tx(full_bar(stage), bytes * NP);
-                  __syncwarp();
-                  if (lane < NP) {
-                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)lane * plane_stride + (int64_t)w * H;
-                    bulk_load_hint(dst + (uint32_t)(lane * box_rows + p.dmax) * 16u, src, bytes, full_bar(stage), pol);
+                  if (leader) {
+                    mbar_expect_tx(full_bar(stage), bytes * NP);
+                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)w * H;
+                    const uint32_t d0 = dst + (uint32_t)p.dmax * 16u;
+#pragma unroll
+                    for (int pl = 0; pl < NP; ++pl)
+                      bulk_load_hint(d0 + (uint32_t)(pl * box_rows) * 16u, src + (int64_t)pl * plane_stride, bytes, full_bar(stage), pol);
                   }
                 } else if (leader) {
                   mbar_expect_tx(full_bar(stage), tx);
@@ -237,7 +302,11 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 if (++stage == p.n_stages) { stage = 0; sphase ^= 1; }
               }
           if (w_pending) request_weights();
+          if (!is_c0) ++wq;
         }
+      }
+      if constexpr (DBG) {
+        if (pdbg && leader) { p.debug[13] = pd_col; p.debug[14] = pd_empty; p.debug[15] = pd_c0; p.debug[7] = pd_issue; }
       }
     }
     __syncwarp();
@@ -285,18 +354,20 @@ resnet_tc_sweep_kernel(const SwParams p) {
       auto stamp = [&](long long& bucket) {
         if constexpr (DBG) { if (dbg) { const long long t = clock64(); bucket += t - dbg_t; dbg_t = t; } }
       };
-      int64_t seq = 0;
+      int64_t sq = 0, wq = 0;   // pseudo-layer / real-layer counters (see the producer)
       for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
-        for (int l = 0; l < n_layers; ++l, ++seq) {
-          const int d = layer_dil(l), box_rows = box_rows_of(d);
+        for (int ll = 0; ll < nl1; ++ll, ++sq) {
+          const bool is_c0 = ll == 0;
+          const int l = ll - 1;
+          const int d = is_c0 ? 1 : layer_dil(l), box_rows = box_rows_of(d);
           const int n_runs = d < W ? d : W;
-          const int cur = (int)(seq & 1);
+          const int cur = (int)(sq & 1);
           const uint32_t plane16 = (uint32_t)box_rows;                       // plane pitch in 16-byte units
           const uint32_t a_lbo = (plane16 & 0x3FFFu) << 16;
-          const uint32_t w16 = ((sbase + p.smem_w_off[cur]) >> 4) + nz;
+          const uint32_t w16 = ((sbase + (is_c0 ? p.smem_c0w_off : p.smem_w_off[wq & 1])) >> 4) + nz;
           const uint32_t row0 = (uint32_t)row0_of(d);
           stamp(dbg_other);
-          mbar_wait_lean(wfull_bar(cur), (uint32_t)((seq >> 1) & 1));
+          if (!is_c0) mbar_wait_lean(wfull_bar((int)(wq & 1)), (uint32_t)((wq >> 1) & 1));
           stamp(dbg_w);
           for (int s = 0; s < n_strips; ++s)
             for (int r = 0; r < n_runs; ++r) {
@@ -319,7 +390,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   stamp(dbg_tempty);
                   mbar_wait_lean(full_bar(stage), sphase);
                   tc_fence_after();
-                  if constexpr (DBG) { if (l == 0 && s == 0 && r == 0 && i < kSwIssuers) stamp(dbg_utt); else stamp(dbg_full); }
+                  if constexpr (DBG) { if (is_c0 && s == 0 && r == 0 && i < kSwIssuers) stamp(dbg_utt); else stamp(dbg_full); }
                   // All operands of the step are computed BEFORE the burst, and the burst is straight-line code
                   // without predicated-off MMAs (separate path for the wrapped window).
                   const uint32_t a16 = ((sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes) >> 4) + row0 + nz;
@@ -335,6 +406,20 @@ resnet_tc_sweep_kernel(const SwParams p) {
                     }
                   if (!leader) {
                     // (only the elected lane issues)
+                  } else if (is_c0) {
+                    // conv_0: one 16-channel chunk (k = 0 .. 2 are its three height taps)
+                    if (wrap_at == n) {
+#pragma unroll
+                      for (int k = 0; k < 3; ++k) umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
+                    } else {
+                      const uint32_t id2 = idesc0 + (uint32_t)(n - wrap_at) * idesc_blk;
+                      const uint32_t bo2 = (uint32_t)wrap_at * blk16;
+#pragma unroll
+                      for (int k = 0; k < 3; ++k) {
+                        umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
+                        umma_f16_lohi<true>(tmem_u, al[k], bl[k] + bo2, desc_hi, id2);
+                      }
+                    }
                   } else if (wrap_at == n) {
 #pragma unroll
                     for (int k = 0; k < 3 * NKC; ++k) umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
@@ -366,14 +451,15 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 if (++sl == NB) { sl = 0; pr ^= 1u; }
               }
             }
-          if (leader) umma_commit(layer_bar(cur));   // every MMA of this layer issued by this warp has retired
+          if (leader) umma_commit(layer_bar(cur));   // every MMA of this pseudo-layer issued by this warp has retired
           __syncwarp();
+          if (!is_c0) ++wq;
         }
       }
       if constexpr (DBG) {
         if (dbg && leader) {
           p.debug[0] = dbg_w; p.debug[1] = dbg_tempty; p.debug[2] = dbg_full; p.debug[3] = dbg_issue;
-          p.debug[4] = n_my; p.debug[5] = dbg_utt; p.debug[6] = dbg_other; p.debug[7] = 0;
+          p.debug[4] = n_my; p.debug[5] = dbg_utt; p.debug[6] = dbg_other;
         }
       }
     }
@@ -387,126 +473,42 @@ resnet_tc_sweep_kernel(const SwParams p) {
     const int et = threadIdx.x;
     int run_pos = 0;
     uint32_t run_par = 0;
-    int64_t seq = 0;
+    int64_t sq = 0;      // pseudo-layer counter (see the producer)
     // cycle accounting of epilogue warp 0 of CTA 0 (HONK2_TC_DEBUG=1)
     const bool edbg = DBG && p.debug != nullptr && blockIdx.x == 0 && warp == 0;
     long long e_wait = 0, e_tmem = 0, e_pub = 0, e_math = 0, e_conv0 = 0, e_t = clock64();
     for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
-      // ------------------------------ conv_0 -> P (resnet.py:40-44) ------------------------------
-      {
-        const float* src = p.feat + b * (int64_t)p.T * p.F;
-        if (p.ph == 1 && p.pw == 1) {
-          // item = (4 consecutive columns, one row); consecutive threads take consecutive rows so that a warp's
-          // 16-byte stores to one (plane, column) are contiguous
-          const int groups = (W + 3) >> 2;
-          for (int item = et; item < H * groups; item += kEpiThreads) {
-            const int gx = item / H, h = item - gx * H, w0 = gx * 4;
-            float pch[3][6];
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-              for (int e = 0; e < 6; ++e) {
-                const int hh = h + a - 1, ww = w0 + e - 1;
-                pch[a][e] = (hh >= 0 && hh < p.T && ww >= 0 && ww < p.F) ? __ldg(src + (int64_t)hh * p.F + ww) : 0.f;
-              }
-            for (int pl = 0; pl < NP; ++pl) {
-              float a4[4][8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float* wc9 = s_w0 + (pl * 8 + e) * 12;
-                const float4 wa = *reinterpret_cast<const float4*>(wc9);
-                const float4 wb = *reinterpret_cast<const float4*>(wc9 + 4);
-                const float w8 = wc9[8];
-#pragma unroll
-                for (int px = 0; px < 4; ++px) {
-                  float v = pch[0][px] * wa.x;
-                  v = fmaf(pch[0][px + 1], wa.y, v); v = fmaf(pch[0][px + 2], wa.z, v);
-                  v = fmaf(pch[1][px], wa.w, v); v = fmaf(pch[1][px + 1], wb.x, v); v = fmaf(pch[1][px + 2], wb.y, v);
-                  v = fmaf(pch[2][px], wb.z, v); v = fmaf(pch[2][px + 1], wb.w, v); v = fmaf(pch[2][px + 2], w8, v);
-                  a4[px][e] = fmaxf(v, 0.f);
-                }
-              }
-#pragma unroll
-              for (int px = 0; px < 4; ++px) {
-                if (w0 + px < W) {
-                  uint4 o;
-                  __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(a4[px][2 * e], a4[px][2 * e + 1]);
-                  uint4* dst = bufP + pl * plane_stride + (int64_t)(w0 + px) * H + h;
-                  if (use_pol) st_hint(dst, o, pol_keep); else *dst = o;
-                }
-              }
-            }
-          }
-        } else {
-          const float inv = 1.f / (float)(p.ph * p.pw);
-          for (int pix = et; pix < H * W; pix += kEpiThreads) {
-            const int wo = pix / H, ho = pix - wo * H;
-            for (int pl = 0; pl < NP; ++pl) {
-              float a8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a8[e] = 0.f;
-              for (int i = 0; i < p.ph; ++i)
-                for (int jj = 0; jj < p.pw; ++jj) {
-                  const int hc = ho * p.ph + i, wc = wo * p.pw + jj;   // centre of the 3x3 window
-                  float xin[9];
-#pragma unroll
-                  for (int a = 0; a < 3; ++a)
-#pragma unroll
-                    for (int e = 0; e < 3; ++e) {
-                      const int hh = hc + a - 1, ww = wc + e - 1;
-                      xin[a * 3 + e] = (hh >= 0 && hh < p.T && ww >= 0 && ww < p.F) ? __ldg(src + (int64_t)hh * p.F + ww) : 0.f;
-                    }
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float* wc9 = s_w0 + (pl * 8 + e) * 12;
-                    const float4 wa = *reinterpret_cast<const float4*>(wc9);
-                    const float4 wb = *reinterpret_cast<const float4*>(wc9 + 4);
-                    float v = xin[0] * wa.x;
-                    v = fmaf(xin[1], wa.y, v); v = fmaf(xin[2], wa.z, v); v = fmaf(xin[3], wa.w, v);
-                    v = fmaf(xin[4], wb.x, v); v = fmaf(xin[5], wb.y, v); v = fmaf(xin[6], wb.z, v);
-                    v = fmaf(xin[7], wb.w, v); v = fmaf(xin[8], wc9[8], v);
-                    a8[e] += fmaxf(v, 0.f);
-                  }
-                }
-              uint4 o;
-              __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(a8[2 * e] * inv, a8[2 * e + 1] * inv);
-              bufP[pl * plane_stride + pix] = o;
-            }
-          }
-        }
-        __threadfence();
-        fence_async_all();   // generic-proxy global writes -> visible to the TMA (async proxy) reads of layer 1
-        __syncwarp();
-        if (lane == 0) mbar_arrive(conv0_bar);
-        if (edbg) { const long long t = clock64(); e_conv0 += t - e_t; e_t = t; }
-      }
-
-      for (int l = 0; l < n_layers; ++l, ++seq) {
-        const int d = layer_dil(l);
+      for (int ll = 0; ll < nl1; ++ll, ++sq) {
+        const bool is_c0 = ll == 0;      // conv_0 + ReLU -> P (resnet.py:40-41): no skip, no constant
+        const int l = ll - 1;
+        const int64_t seq = sq;
+        const int d = is_c0 ? 1 : layer_dil(l);
         const int n_runs = d < W ? d : W;
-        const int cur = (int)(seq & 1);
-        const float* kconst = reinterpret_cast<const float*>(p.kconst0 + l * p.layer_stride);
+        const int cur = (int)(sq & 1);
         float kc_reg[16];
+        if (is_c0) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) kc_reg[c] = __ldg(kconst + 16 * j + c);
+          for (int c = 0; c < 16; ++c) kc_reg[c] = 0.f;
+        } else {
+          const float* kconst = reinterpret_cast<const float*>(p.kconst0 + l * p.layer_stride);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) kc_reg[c] = __ldg(kconst + 16 * j + c);
+        }
         // The layer body is instantiated per (skip, pooling) variant so that the registers of the skip prefetch
         // and of the pooled sums are not live together.
         auto layer_body = [&](auto skip_c, auto last_c) {
           constexpr bool HAS_SKIP = decltype(skip_c)::value;   // odd l: adds the skip tensor from P, stores to P in place
           constexpr bool LAST = decltype(last_c)::value;       // pooled instead of stored
           const uint4* skip_in = bufP + (int64_t)(2 * j) * plane_stride;
-          uint4* y_out = (HAS_SKIP ? bufP : bufQ) + (int64_t)(2 * j) * plane_stride;
-          const uint64_t pol_out = HAS_SKIP ? pol_keep : pol_stream;
+          const bool to_p = HAS_SKIP || is_c0;   // conv_0 and the skip layers write P, the others Q
+          uint4* y_out = (to_p ? bufP : bufQ) + (int64_t)(2 * j) * plane_stride;
+          const uint64_t pol_out = to_p ? pol_keep : pol_stream;
           float psum[LAST ? 16 : 1];
 #pragma unroll
           for (int c = 0; c < (LAST ? 16 : 1); ++c) psum[c] = 0.f;
           // this layer overwrites the buffer the previous layer READS through TMA: wait until all of its MMAs
           // (hence all of its loads) have retired before the first store
-          bool guard = l > 0;
+          bool guard = sq > 0;
           int pending_w = -1;   // column whose stores still have to be published (one block behind)
           auto publish = [&](int wcol) {
             // generic-proxy global stores of this thread -> visible to the async proxy (the TMA loads of the next
@@ -627,7 +629,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
             }
           }
         };
-        const bool has_skip = (l & 1) != 0, last = l == n_layers - 1;
+        const bool has_skip = !is_c0 && (l & 1) != 0, last = l == n_layers - 1;
         if (has_skip) { if (last) layer_body(std::true_type{}, std::true_type{}); else layer_body(std::true_type{}, std::false_type{}); }
         else { if (last) layer_body(std::false_type{}, std::true_type{}); else layer_body(std::false_type{}, std::false_type{}); }
       }
