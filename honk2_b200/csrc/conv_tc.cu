@@ -1329,6 +1329,8 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W) {
   const kws_resnet_config& c = p->cfg;
   if (!p->sweep_enabled || c.n_layers < 1 || c.n_layers > kFusedMaxLayers || c.n_labels > 4096) return f;
   if (W < 1 || W > kSwMaxW || H < 1) return f;
+  if (p->NKC > 3) return f;   // 64 maps: 640 threads leave 96 registers, the epilogue spills (position-major kernel instead)
+  if ((1 + c.n_layers) * p->CP * 4 > kSwKcBytes) return f;   // per-layer epilogue constants live in shared memory
   if (c.pool_h > 1 || c.pool_w > 1) return f;   // conv_0 runs as a tensor-core pseudo-layer on the unpooled map
   f.n_strips = ceil_div(H, 128);
   // the 128 lanes of an MMA are 128 rows of one column: short maps (res8 / res26 after pooling) would leave
@@ -1460,13 +1462,35 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
     if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
     prm.debug = dbg_buf;
   }
+  if (dbg_on) { const char* e = std::getenv("HONK2_TC_DIAG"); prm.diag = e ? std::atoi(e) : 0; }
+  static const bool trace_on = [] { const char* e = std::getenv("HONK2_TC_TRACE"); return e && std::atoi(e) != 0; }();
+  static long long* trace_buf = nullptr;
+  if (dbg_on && trace_on) {
+    if (!trace_buf) { cudaMalloc(&trace_buf, 8 * kSwTraceLen * sizeof(long long)); }
+    cudaMemsetAsync(trace_buf, 0, 8 * kSwTraceLen * sizeof(long long), st);
+    prm.trace = trace_buf;
+  }
   struct DbgPrint {
-    long long* buf; cudaStream_t st;
+    long long* buf; cudaStream_t st; long long* trace;
     ~DbgPrint() {
       if (!buf) return;
       long long h[16];
       cudaStreamSynchronize(st);
       cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+      if (trace) {   // event timestamps of CTA 0 -> HONK2_TC_TRACE_FILE (one row per event kind)
+        std::vector<long long> t(8 * kSwTraceLen);
+        cudaMemcpy(t.data(), trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        const char* fn = std::getenv("HONK2_TC_TRACE_FILE");
+        if (FILE* f = fopen(fn ? fn : "sweep_trace.csv", "w")) {
+          fprintf(f, "idx,producer_copy,issuer_start,issuer_after_tempty,issuer_after_full,issuer_after_issue,epi0_tfull,epi0_done,epi7_done\n");
+          for (int i = 0; i < kSwTraceLen; ++i) {
+            fprintf(f, "%d", i);
+            for (int r = 0; r < 8; ++r) fprintf(f, ",%lld", t[(size_t)r * kSwTraceLen + i]);
+            fprintf(f, "\n");
+          }
+          fclose(f);
+        }
+      }
       const double ptot = (double)(h[13] + h[14] + h[15] + h[7]);
       fprintf(stderr, "[sweep dbg] producer of CTA 0: waiting for the previous layer's column %.1f%%, for a free stage %.1f%%, building "
               "conv_0 columns %.1f%%, issuing copies / weights / bookkeeping %.1f%% (total %.0f)\n",
@@ -1483,7 +1507,7 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
               "previous column %.1f%%, math + stores (+ guard, tail) %.1f%%, conv_0 %.1f%% (total %.0f)\n",
               100 * h[8] / et, 100 * h[9] / et, 100 * h[10] / et, 100 * h[11] / et, 100 * h[12] / et, et);
     }
-  } dbg_print{dbg_on ? dbg_buf : nullptr, st};
+  } dbg_print{dbg_on ? dbg_buf : nullptr, st, prm.trace};
   switch (p->NKC) {
     case 1: return tc_launch_sweep<1>(prm, grid, p->sweep_smem, st);
     case 2: return tc_launch_sweep<2>(prm, grid, p->sweep_smem, st);

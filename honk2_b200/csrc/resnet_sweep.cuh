@@ -46,6 +46,7 @@ constexpr int kSwIssuers = 3;       // issuer m issues the MMAs of height tap dh
 constexpr int kSwMaxStages = 12;
 constexpr int kSwMaxRing = 32;
 constexpr int kSwMaxW = 256;
+constexpr int kSwTraceLen = 2048;   // steps / blocks recorded by the event trace
 constexpr int kSwWeightStep = 12;   // producer step of a layer at which the NEXT layer's weights are requested
 
 __host__ __device__ constexpr int sw_epi_warps(int NKC) { return 4 * NKC; }
@@ -64,7 +65,10 @@ constexpr int kSwTmemSlot = kSwBarCol + 8 * 2 * kSwMaxW;       // u32
 constexpr int kSwZero = kSwTmemSlot + 4;                       // u32, always 0 (see the MMA issuers)
 constexpr int kSwPool = round_up(kSwZero + 4, 128);            // [64] f32 pooled sums
 constexpr int kSwW0 = kSwPool + 256;                           // [64][12] f32 conv_0 weights
-constexpr int kSwCtrlBytes = round_up(kSwW0 + 64 * 12 * 4, 1024);
+constexpr int kSwKc = kSwW0;                                   // [1 + n_layers][CP] f32 epilogue constants (row 0 = conv_0 = zeros)
+constexpr int kSwKcBytes = 7168;
+constexpr int kSwCtrlBytes = round_up(kSwKc + kSwKcBytes, 1024);
+// (epilogue warp group g = warp / 4, one warp per TMEM lane quarter, owns the blocks = g mod NKC: there are NKC groups)
 
 struct SwParams {
   // Per-layer data is derived from kernel parameters only (constant bank => warp-uniform for the compiler, which
@@ -94,7 +98,9 @@ struct SwParams {
                                 //   into a fixed [plane][128 + 2 dmax] slot whose pad rows stay zero; 0: TMA tensor boxes
   int dmax;                     // largest dilation of the network (bulk path: data row h sits at slot row dmax + h)
   int issue_style;              // 0: MMA operands in uniform registers, 1: ordinary registers + R2UR (experiments)
-  long long* debug;             // optional [8] cycle counters of CTA 0's issuer
+  int diag;                     // diagnostics (wrong results!): 1 = epilogue skips math and stores, 2 = skips the skip-tensor loads
+  long long* debug;             // optional cycle counters of CTA 0 (HONK2_TC_DEBUG=1)
+  long long* trace;             // optional [8][kSwTraceLen] event timestamps of CTA 0 (HONK2_TC_TRACE=1, needs DEBUG)
 };
 
 template <int NKC, bool DBG>
@@ -133,10 +139,10 @@ resnet_tc_sweep_kernel(const SwParams p) {
   // ---- one-time setup
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < NB; ++a) { mbar_init(tfull_bar(a), kSwIssuers); mbar_init(tempty_bar(a), kEpiWarps); }
+    for (int a = 0; a < NB; ++a) { mbar_init(tfull_bar(a), kSwIssuers); mbar_init(tempty_bar(a), 4); }
     for (int i = 0; i < 2; ++i) { mbar_init(wfull_bar(i), 1); mbar_init(layer_bar(i), kSwIssuers); }
     for (int par = 0; par < 2; ++par)
-      for (int w = 0; w < W; ++w) mbar_init(col_bar(par, w), (uint32_t)(kEpiWarps * n_strips));
+      for (int w = 0; w < W; ++w) mbar_init(col_bar(par, w), (uint32_t)(4 * n_strips));
     fence_barrier_init();
   }
   if (threadIdx.x == 32) *reinterpret_cast<volatile uint32_t*>(smem + kSwZero) = 0u;
@@ -147,6 +153,14 @@ resnet_tc_sweep_kernel(const SwParams p) {
     for (int i = threadIdx.x; i < (3 * W_SLAB) / 16; i += sw_threads(NKC)) dst[i] = src[i];
   }
   for (int i = threadIdx.x; i < CP; i += sw_threads(NKC)) s_pool[i] = 0.f;
+  {   // epilogue constants of every pseudo-layer, read from shared memory at use
+      // (the host plan guarantees (1 + n_layers) * CP * 4 <= kSwKcBytes)
+    float* s_kc = reinterpret_cast<float*>(smem + kSwKc);
+    for (int i = threadIdx.x; i < nl1 * CP; i += sw_threads(NKC)) {
+      const int ll = i / CP, c = i - ll * CP;
+      s_kc[i] = ll == 0 ? 0.f : reinterpret_cast<const float*>(p.kconst0 + (ll - 1) * p.layer_stride)[c];
+    }
+  }
   if (p.bulk_rows > 0) {
     // bulk-copy staging: the pad rows above and below the map are never written again and supply the zero padding
     uint4* ring = reinterpret_cast<uint4*>(smem + p.smem_ring_off);
@@ -193,6 +207,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
       int64_t sq = 0;      // pseudo-layer counter (conv_0 included): parity of the layer / column barriers
       int64_t wq = 0;      // real-layer counter: parity of the weight buffers
       const bool pdbg = DBG && p.debug != nullptr && blockIdx.x == 0;
+      const bool ptrace = DBG && p.trace != nullptr && blockIdx.x == 0;
+      int pstep = 0;
       long long pd_col = 0, pd_empty = 0, pd_c0 = 0, pd_issue = 0, pd_t = DBG ? clock64() : 0;
       auto pstamp = [&](long long& bucket) {
         if constexpr (DBG) { if (pdbg) { const long long t = clock64(); bucket += t - pd_t; pd_t = t; } }
@@ -299,6 +315,10 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   if (use_pol) tma_load_4d_hint(dst, map, full_bar(stage), 0, s * 128 - d, w, (int)blockIdx.x * NP, pol);
                   else tma_load_4d(dst, map, full_bar(stage), 0, s * 128 - d, w, (int)blockIdx.x * NP);
                 }
+                if constexpr (DBG) {
+                  if (ptrace && leader && pstep < kSwTraceLen) p.trace[0 * kSwTraceLen + pstep] = clock64();
+                  ++pstep;
+                }
                 if (++stage == p.n_stages) { stage = 0; sphase ^= 1; }
               }
           if (w_pending) request_weights();
@@ -351,6 +371,11 @@ resnet_tc_sweep_kernel(const SwParams p) {
       constexpr uint32_t blk16 = BLK_BYTES >> 4;
       long long dbg_full = 0, dbg_tempty = 0, dbg_issue = 0, dbg_w = 0, dbg_utt = 0, dbg_other = 0, dbg_t = DBG ? clock64() : 0;
       const bool dbg = DBG && p.debug != nullptr && blockIdx.x == 0 && me == 0;
+      const bool itrace = DBG && p.trace != nullptr && blockIdx.x == 0;
+      int gstep = 0;
+      auto tr = [&](int row) {
+        if constexpr (DBG) { if (itrace && leader && gstep < kSwTraceLen) p.trace[row * kSwTraceLen + gstep] = clock64(); }
+      };
       auto stamp = [&](long long& bucket) {
         if constexpr (DBG) { if (dbg) { const long long t = clock64(); bucket += t - dbg_t; dbg_t = t; } }
       };
@@ -383,13 +408,16 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   const int wrap_at = NB - p0 < n ? NB - p0 : n;              // blocks before the ring wraps
                   const int blk0 = lo ? 0 : 1;                                 // weight block of the first window block
                   stamp(dbg_other);
+                  tr(1);
                   // the epilogue must have drained and re-zeroed the previous use of every slot of the window
                   if (lo) mbar_wait_lean(tempty_bar(s_lo), par_lo ^ 1u);
                   mbar_wait_lean(tempty_bar(sl), pr ^ 1u);
                   if (hi_) mbar_wait_lean(tempty_bar(s_hi), par_hi ^ 1u);
                   stamp(dbg_tempty);
+                  tr(2);
                   mbar_wait_lean(full_bar(stage), sphase);
                   tc_fence_after();
+                  tr(3);
                   if constexpr (DBG) { if (is_c0 && s == 0 && r == 0 && i < kSwIssuers) stamp(dbg_utt); else stamp(dbg_full); }
                   // All operands of the step are computed BEFORE the burst, and the burst is straight-line code
                   // without predicated-off MMAs (separate path for the wrapped window).
@@ -445,7 +473,9 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   }
                   __syncwarp();
                   stamp(dbg_issue);
+                  tr(4);
                 }
+                ++gstep;
                 if (++owner == kSwIssuers) owner = 0;
                 if (++stage == p.n_stages) { stage = 0; sphase ^= 1; }
                 if (++sl == NB) { sl = 0; pr ^= 1u; }
@@ -468,14 +498,24 @@ resnet_tc_sweep_kernel(const SwParams p) {
     // ========================================= epilogue (4*NKC warps) =========================================
     // warp e: TMEM lane quarter q = warp % 4 (rows q*32 .. q*32+31 of the strip), channel group j = e / 4
     // (16 channels = planes 2j, 2j+1).  One block = one output column of one strip.
+    // Warp (q, g): TMEM lane quarter q = warp % 4 (rows q*32 .. q*32+31 of the strip), group g = warp / 4.  One block =
+    // one output column of one strip.  Group g owns every block whose running index is g mod NKC and handles ALL of its
+    // channels, 16 at a time: the per-visit costs (barrier wait, slot hand-back, publishing, the latency of the first
+    // TMEM load) are paid once per three blocks and per 48 channels instead of once per block and per 16 (the
+    // epilogue's store/math phase, not the tensor pipe, bounded the kernel: with it disabled the same schedule ran
+    // 34 % faster), and the skip tensor of the next own block is prefetched a whole two block periods ahead with a
+    // single register set.
     const int q = warp & 3;
-    const int j = warp >> 2;
+    const int g = warp >> 2;
     const int et = threadIdx.x;
-    int run_pos = 0;
-    uint32_t run_par = 0;
+    int esl = 0;         // ring slot of the block the iterator stands on
+    uint32_t epr = 0;    // its use parity
+    int eown = 0;        // which group owns it
     int64_t sq = 0;      // pseudo-layer counter (see the producer)
     // cycle accounting of epilogue warp 0 of CTA 0 (HONK2_TC_DEBUG=1)
     const bool edbg = DBG && p.debug != nullptr && blockIdx.x == 0 && warp == 0;
+    const bool etrace = DBG && p.trace != nullptr && blockIdx.x == 0 && (warp == 0 || warp == 7) && lane == 0;
+    int gblk = 0;
     long long e_wait = 0, e_tmem = 0, e_pub = 0, e_math = 0, e_conv0 = 0, e_t = clock64();
     for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
       for (int ll = 0; ll < nl1; ++ll, ++sq) {
@@ -485,147 +525,149 @@ resnet_tc_sweep_kernel(const SwParams p) {
         const int d = is_c0 ? 1 : layer_dil(l);
         const int n_runs = d < W ? d : W;
         const int cur = (int)(sq & 1);
-        float kc_reg[16];
-        if (is_c0) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) kc_reg[c] = 0.f;
-        } else {
-          const float* kconst = reinterpret_cast<const float*>(p.kconst0 + l * p.layer_stride);
-#pragma unroll
-          for (int c = 0; c < 16; ++c) kc_reg[c] = __ldg(kconst + 16 * j + c);
-        }
+        const uint32_t kc_addr = sbase + kSwKc + (uint32_t)(ll * CP) * 4u;
         // The layer body is instantiated per (skip, pooling) variant so that the registers of the skip prefetch
         // and of the pooled sums are not live together.
         auto layer_body = [&](auto skip_c, auto last_c) {
           constexpr bool HAS_SKIP = decltype(skip_c)::value;   // odd l: adds the skip tensor from P, stores to P in place
           constexpr bool LAST = decltype(last_c)::value;       // pooled instead of stored
-          const uint4* skip_in = bufP + (int64_t)(2 * j) * plane_stride;
+          const uint4* skip_in = bufP;
           const bool to_p = HAS_SKIP || is_c0;   // conv_0 and the skip layers write P, the others Q
-          uint4* y_out = (to_p ? bufP : bufQ) + (int64_t)(2 * j) * plane_stride;
+          uint4* y_out = to_p ? bufP : bufQ;
           const uint64_t pol_out = to_p ? pol_keep : pol_stream;
-          float psum[LAST ? 16 : 1];
+          float psum[LAST ? CP : 1];
 #pragma unroll
-          for (int c = 0; c < (LAST ? 16 : 1); ++c) psum[c] = 0.f;
+          for (int c = 0; c < (LAST ? CP : 1); ++c) psum[c] = 0.f;
           // this layer overwrites the buffer the previous layer READS through TMA: wait until all of its MMAs
           // (hence all of its loads) have retired before the first store
           bool guard = sq > 0;
-          int pending_w = -1;   // column whose stores still have to be published (one block behind)
+          int pending_w = -1;   // column whose stores still have to be published (one visit behind)
           auto publish = [&](int wcol) {
-            // generic-proxy global stores of this thread -> visible to the async proxy (the TMA loads of the next
-            // layer, issued by this CTA's producer after it acquires the column barrier).  The all-space
-            // fence.proxy.async compiles to MEMBAR.ALL.GPU and, issued by 12 warps per column, stalls the whole
-            // SM; the .global form is a plain view fence.
+            // generic-proxy global stores of this thread -> visible to the async proxy (the bulk copies / TMA loads of the
+            // next layer, issued by this CTA's producer after it acquires the column barrier).  The all-space
+            // fence.proxy.async compiles to MEMBAR.ALL.GPU and stalls the whole SM; the .global form is a view fence.
             fence_async_global();
             __syncwarp();
             if (lane == 0) mbar_arrive(col_bar(cur, wcol));
           };
-          // block iterator over (strip, run, output column of the run)
+          // block iterator over (strip, run, output column of the run); every warp walks all blocks, works on its own
           struct It { int s, r, o, Lr, w; bool done; };
-          auto it_begin = [&]() { It it; it.s = 0; it.r = 0; it.o = 0; it.Lr = (W + d - 1) / d; it.w = 0; it.done = false; return it; };
-          auto it_next = [&](It it) {
-            ++it.o; it.w += d;
-            if (it.o == it.Lr) {
-              it.o = 0;
-              if (++it.r == n_runs) { it.r = 0; if (++it.s == n_strips) it.done = true; }
-              it.w = it.r;
-              it.Lr = (W - it.r + d - 1) / d;
+          struct Own { int off, w, slot; uint32_t par; bool exists; };   // off: this lane's position inside a plane, -1 outside the map
+          It it; it.s = 0; it.r = 0; it.o = 0; it.Lr = (W + d - 1) / d; it.w = 0; it.done = false;
+          auto next_own = [&]() {   // advance to this group's next block (consuming it) and describe it
+            Own ob; ob.exists = false; ob.off = -1; ob.w = 0; ob.slot = 0; ob.par = 0;
+            while (!it.done) {
+              const bool mine = eown == g;
+              if (mine) {
+                const int row = it.s * 128 + q * 32 + lane;
+                ob.exists = true; ob.w = it.w; ob.slot = esl; ob.par = epr;
+                ob.off = row < H ? it.w * H + row : -1;
+              }
+              // step the iterator, the ring slot and the owner
+              ++it.o; it.w += d;
+              if (it.o == it.Lr) {
+                it.o = 0;
+                if (++it.r == n_runs) { it.r = 0; if (++it.s == n_strips) it.done = true; }
+                it.w = it.r;
+                it.Lr = (W - it.r + d - 1) / d;
+              }
+              if (++esl == NB) { esl = 0; epr ^= 1u; }
+              if (++eown == NKC) eown = 0;
+              if (mine) break;
             }
-            return it;
+            return ob;
           };
-          auto load_skip = [&](uint4 (&pv)[2], const It& it) {
+          auto load_skip = [&](uint4 (&pv)[NP], const Own& ob) {
             if constexpr (HAS_SKIP) {
-              const int row = it.s * 128 + q * 32 + lane;
-              if (!it.done && row < H) {
-                const int64_t off = (int64_t)it.w * H + row;
-                pv[0] = use_pol ? ld_hint(skip_in + off, pol_keep) : skip_in[off];
-                pv[1] = use_pol ? ld_hint(skip_in + off + plane_stride, pol_keep) : skip_in[off + plane_stride];
+              if (ob.off >= 0 && !(DBG && (p.diag & 2))) {
+#pragma unroll
+                for (int pl = 0; pl < NP; ++pl)
+                  pv[pl] = use_pol ? ld_hint(skip_in + (int64_t)pl * plane_stride + ob.off, pol_keep)
+                                   : skip_in[(int64_t)pl * plane_stride + ob.off];
               }
             }
           };
-          auto process = [&](const It& it, const uint4 (&pv)[2]) {
-            const int row = it.s * 128 + q * 32 + lane;
-            const bool valid = row < H;
-            const int64_t off = (int64_t)it.w * H + row;
-            const int t = run_pos + it.o, qd = t / NB, pos = t - qd * NB;
-            mbar_wait_sleepy(tfull_bar(pos), run_par ^ (uint32_t)(qd & 1));
+          auto process = [&](const Own& ob, const uint4 (&pv)[NP]) {
+            const bool valid = ob.off >= 0;
+            mbar_wait_sleepy(tfull_bar(ob.slot), ob.par);
             tc_fence_after();
+            if constexpr (DBG) { if (etrace && warp == 0 && gblk < kSwTraceLen) p.trace[5 * kSwTraceLen + gblk] = clock64(); }
             if (edbg) { const long long t = clock64(); e_wait += t - e_t; e_t = t; }
-            uint32_t v[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(pos * CP + 16 * j);
-            tmem_ld16(taddr, v);
-            tmem_ld_wait();
-            tmem_st16_zero(taddr);   // the next user of this ring slot accumulates from zero
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(pos));   // accumulators are in registers, the slot is zero again: free
-            if (edbg) { const long long t = clock64(); e_tmem += t - e_t; e_t = t; }
             if (pending_w >= 0) { publish(pending_w); pending_w = -1; }
             if (edbg) { const long long t = clock64(); e_pub += t - e_t; e_t = t; }
             if (guard) {
               mbar_wait_sleepy(layer_bar(cur ^ 1), (uint32_t)(((seq - 1) >> 1) & 1));
               guard = false;
             }
-            if (valid) {
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ob.slot * CP);
 #pragma unroll
-              for (int hf = 0; hf < 2; ++hf) {
-                float x[8];
+            for (int jj = 0; jj < NKC; ++jj) {
+              uint32_t v[16];
+              tmem_ld16(tbase + 16 * jj, v);
+              tmem_ld_wait();
+              tmem_st16_zero(tbase + 16 * jj);   // the next user of this ring slot accumulates from zero
+              if (jj == NKC - 1) {
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(ob.slot));   // all channels are in registers / stored, the slot is zero again
+              }
+              if (valid && !(DBG && (p.diag & 1))) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[8 * hf + e]), 0.f) + kc_reg[8 * hf + e];
-                if constexpr (HAS_SKIP) {
-                  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[hf]);
+                for (int hf = 0; hf < 2; ++hf) {
+                  float x[8], kc8[8];   // constants read at use (volatile: not hoisted into registers for the whole layer)
+                  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(kc8[0]), "=f"(kc8[1]), "=f"(kc8[2]), "=f"(kc8[3]) : "r"(kc_addr + (uint32_t)(64 * jj + 32 * hf)));
+                  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(kc8[4]), "=f"(kc8[5]), "=f"(kc8[6]), "=f"(kc8[7]) : "r"(kc_addr + (uint32_t)(64 * jj + 32 * hf + 16)));
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(pb[e]);
-                    x[2 * e] += f.x;
-                    x[2 * e + 1] += f.y;
+                  for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[8 * hf + e]), 0.f) + kc8[e];
+                  if constexpr (HAS_SKIP) {
+                    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[2 * jj + hf]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f = __bfloat1622float2(pb[e]);
+                      x[2 * e] += f.x;
+                      x[2 * e + 1] += f.y;
+                    }
                   }
-                }
-                if constexpr (LAST) {
+                  if constexpr (LAST) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) psum[8 * hf + e] += x[e];
-                } else {
-                  uint4 yo;
-                  __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
+                    for (int e = 0; e < 8; ++e) psum[16 * jj + 8 * hf + e] += x[e];
+                  } else {
+                    uint4 yo;
+                    __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-                  if (use_pol) st_hint(y_out + off + hf * plane_stride, yo, pol_out);
-                  else y_out[off + hf * plane_stride] = yo;
+                    for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+                    uint4* dst = y_out + (int64_t)(2 * jj + hf) * plane_stride + ob.off;
+                    if (use_pol) st_hint(dst, yo, pol_out);
+                    else *dst = yo;
+                  }
                 }
               }
             }
             if (edbg) { const long long t = clock64(); e_math += t - e_t; e_t = t; }
-            pending_w = it.w;
-            if (it.o == it.Lr - 1) {   // run finished: advance the ring bookkeeping
-              const int t2 = run_pos + it.Lr, q2 = t2 / NB;
-              run_pos = t2 - q2 * NB;
-              run_par ^= (uint32_t)(q2 & 1);
+            if constexpr (DBG) {
+              if (etrace && gblk < kSwTraceLen) p.trace[(warp == 0 ? 6 : 7) * kSwTraceLen + gblk] = clock64();
+              ++gblk;
             }
+            pending_w = ob.w;
           };
-          // The skip tensor is prefetched two blocks ahead (two register sets, the loop is unrolled by two) so that
-          // its L2 latency hides behind a whole block period.
-          uint4 pa[2], pb2[2];
-          It ia = it_begin(), ib = it_next(ia);
-          load_skip(pa, ia);
-          load_skip(pb2, ib);
-          while (!ia.done) {
-            process(ia, pa);
-            ia = it_next(ib);
-            load_skip(pa, ia);
-            if (ib.done) break;
-            process(ib, pb2);
-            ib = it_next(ia);
-            load_skip(pb2, ib);
+          uint4 pv[NP];
+          Own ob = next_own();
+          load_skip(pv, ob);
+          while (ob.exists) {
+            process(ob, pv);
+            ob = next_own();
+            load_skip(pv, ob);   // the next own block is three blocks away: two block periods of prefetch distance
           }
           if (pending_w >= 0) publish(pending_w);
           if constexpr (LAST) {
             // fused global mean (resnet.py:57-58): warp-reduce the 32 rows, one shared atomic per channel
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
+            for (int c = 0; c < CP; ++c) {
               float sum = psum[c];
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-              if (lane == c) atomicAdd(s_pool + 16 * j + c, sum);
+              if (lane == (c & 31)) atomicAdd(s_pool + c, sum);
             }
           }
         };

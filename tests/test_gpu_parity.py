@@ -328,3 +328,34 @@ def test_bf16_column_sweep_kernel_matches_position_major_kernel_at_full_batch(de
     idx = np.random.default_rng(2).choice(8192, 8, replace=False)
     ref = model_ref.forward(kind, sd, cfg, feats[torch.from_numpy(idx).to(dev)].cpu()).numpy()
     assert logit_err(ys[0][torch.from_numpy(idx).to(dev)].cpu().numpy(), ref) <= BF16_TOL
+
+
+@pytest.mark.parametrize("name", ["res15", "res15_narrow"])
+def test_bf16_resnet_other_time_lengths(dev, name, model_golden):
+    """T = 301 frames: the column-sweep kernel runs three 128-row strips per column and stages them with TMA boxes
+    (the 1-D bulk-copy staging is the single-strip case); checked against the reference golden."""
+    m, _ = gpu_model(name, "hardened", dev, precision="bf16")
+    with torch.no_grad():
+        y = m(torch.from_numpy(model_golden["feats_long"]).to(dev)).cpu().numpy()
+    ref = model_golden[f"{name}/hardened/logits_long"]
+    assert np.isfinite(y).all()
+    assert logit_err(y, ref) <= BF16_TOL, logit_err(y, ref)
+
+
+def test_bf16_res15_hey_snips_shaped_clips(dev):
+    """BASELINE config 5 shape: 9 s clips (144 000 samples -> 901 x 40), res15 with 2 labels, waveform -> logits,
+    against the CPU oracle on the same seeded clips."""
+    kind, cfg = model_config("res15", n_labels=2)
+    m = honk2_b200.build_model("res15", n_labels=2, precision="bf16")
+    sd = m.state_dict()
+    synth.harden_(sd)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    w = synth.broadband(3, N=144000, seed=31)
+    ref = model_ref.forward(kind, {k: v.clone() for k, v in sd.items()}, cfg,
+                            torch.from_numpy(mfcc_ref.compute_mfccs_batch(w))).numpy()
+    ap = AudioProcessor()
+    with torch.no_grad():
+        y = m.forward_wave(torch.from_numpy(w).to(dev), ap).cpu().numpy()
+    assert y.shape == (3, 2) and np.isfinite(y).all()
+    assert logit_err(y, ref) <= BF16_TOL, logit_err(y, ref)
