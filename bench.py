@@ -77,9 +77,11 @@ class ClockSampler:
         self.proc = None
 
     def start(self):
+        # started BEFORE the warm-up (nvidia-smi needs ~0.3 s to produce its first row) and sampled every 20 ms; every
+        # row is tagged with the host time it arrived at, stop() keeps the rows that fall inside the timed region
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -88,9 +90,9 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, window=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -101,7 +103,16 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows, note = [r for _, r in self.rows], None
+        if window is not None:
+            t0, t1 = window
+            inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.03]
+            if inside:
+                rows = inside
+            else:   # region shorter than the sampling period: nearest rows (the GPU is under the same load in the warm-up)
+                rows = [r for t, r in self.rows if t0 - 0.25 <= t <= t1 + 0.25]
+                note = "no sample fell inside the timed region; rows within 0.25 s of it"
+        for r in rows:
             if len(r) < 7:
                 continue
             try:
@@ -111,8 +122,11 @@ class ClockSampler:
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def cpu_reference_step(model_name, n_utts, seed):
@@ -246,22 +260,24 @@ def main():
         torch.cuda.synchronize()
 
     with torch.no_grad():
-        for i in range(W):
-            step_device(i)
-        barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        for i in range(W):
+            step_device(i)
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = 0
+        t_host0 = time.perf_counter()
         e0.record()
         for i in range(K):
             step_device(i)
             launches += model.last_launches(dev) + 1 + (2 if world > 1 else 0)
         e1.record()
         barrier()
+        t_host1 = time.perf_counter()
         ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop((t_host0, t_host1)) if rank == 0 else None
         t = torch.tensor([ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
