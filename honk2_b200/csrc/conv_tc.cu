@@ -161,6 +161,19 @@ __device__ __forceinline__ uint4 ld_hint(const uint4* ptr, uint64_t pol) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol) : "memory");
   return v;
 }
+// L2-only (.cg) variant: for data another warp of this CTA stored (no reliance on L1 seeing that store)
+__device__ __forceinline__ uint4 ld_cg_hint(const uint4* ptr, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_cg(const uint4* ptr) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_hint(uint4* ptr, const uint4& v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
                ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");

@@ -538,9 +538,14 @@ resnet_tc_sweep_kernel(const SwParams p) {
           float psum[LAST ? CP : 1];
 #pragma unroll
           for (int c = 0; c < (LAST ? CP : 1); ++c) psum[c] = 0.f;
-          // this layer overwrites the buffer the previous layer READS through TMA: wait until all of its MMAs
-          // (hence all of its loads) have retired before the first store
-          bool guard = sq > 0;
+          // Before touching this layer: wait until every MMA of the previous pseudo-layer has retired.  (1) This layer
+          // overwrites the buffer the previous one READS through bulk copies / TMA, so no store may precede that.
+          // (2) The skip tensor prefetched below was stored two pseudo-layers ago, possibly by ANOTHER warp group that
+          // this one has overtaken (block ownership rotates; with very short layers a group can have no block in a
+          // layer at all); the previous layer's MMAs having retired implies that all of its inputs were copied, hence
+          // that every column of the layer before it had been stored and published.  The wait is free: none of this
+          // warp's blocks of this layer can be complete earlier.
+          if (sq > 0) mbar_wait_sleepy(layer_bar(cur ^ 1), (uint32_t)(((seq - 1) >> 1) & 1));
           int pending_w = -1;   // column whose stores still have to be published (one visit behind)
           auto publish = [&](int wcol) {
             // generic-proxy global stores of this thread -> visible to the async proxy (the bulk copies / TMA loads of the
@@ -582,8 +587,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
               if (ob.off >= 0 && !(DBG && (p.diag & 2))) {
 #pragma unroll
                 for (int pl = 0; pl < NP; ++pl)
-                  pv[pl] = use_pol ? ld_hint(skip_in + (int64_t)pl * plane_stride + ob.off, pol_keep)
-                                   : skip_in[(int64_t)pl * plane_stride + ob.off];
+                  pv[pl] = use_pol ? ld_cg_hint(skip_in + (int64_t)pl * plane_stride + ob.off, pol_keep)
+                                   : ld_cg(skip_in + (int64_t)pl * plane_stride + ob.off);   // (stored by another warp: L2, not L1)
               }
             }
           };
@@ -595,10 +600,6 @@ resnet_tc_sweep_kernel(const SwParams p) {
             if (edbg) { const long long t = clock64(); e_wait += t - e_t; e_t = t; }
             if (pending_w >= 0) { publish(pending_w); pending_w = -1; }
             if (edbg) { const long long t = clock64(); e_pub += t - e_t; e_t = t; }
-            if (guard) {
-              mbar_wait_sleepy(layer_bar(cur ^ 1), (uint32_t)(((seq - 1) >> 1) & 1));
-              guard = false;
-            }
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ob.slot * CP);
 #pragma unroll
             for (int jj = 0; jj < NKC; ++jj) {

@@ -359,3 +359,19 @@ def test_bf16_res15_hey_snips_shaped_clips(dev):
         y = m.forward_wave(torch.from_numpy(w).to(dev), ap).cpu().numpy()
     assert y.shape == (3, 2) and np.isfinite(y).all()
     assert logit_err(y, ref) <= BF16_TOL, logit_err(y, ref)
+
+
+@pytest.mark.parametrize("T,F,B", [(100, 8, 5), (128, 3, 2), (129, 17, 3), (97, 1, 4)])
+def test_bf16_sweep_kernel_odd_map_shapes(dev, T, F, B):
+    """Maps narrower than the dilation (every run is a single column: one-block windows, both stand-in arrivals),
+    layers with fewer steps than the weight-prefetch step, a strip boundary at exactly 128 rows and one row more,
+    a single-column map: all against the CPU oracle (res15 topology, 13 layers, dilation up to 16)."""
+    kind, cfg = model_config("res15")
+    m, sd = gpu_model("res15", "hardened", dev, precision="bf16")
+    g = torch.Generator().manual_seed(T * 100 + F)
+    x = torch.randn(B, T, F, generator=g) * 3.0 - 8.0
+    ref = model_ref.forward(kind, sd, cfg, x).numpy()
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu().numpy()
+    assert np.isfinite(y).all()
+    assert logit_err(y, ref) <= BF16_TOL, logit_err(y, ref)
