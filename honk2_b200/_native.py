@@ -63,6 +63,8 @@ SIGNATURES = {
                                          C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kws_model_last_launches": (C.c_int64, [C.c_void_p]),
     "kws_model_kernel_path": (C.c_char_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "kws_eval_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "kws_model_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "kws_model_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                          C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

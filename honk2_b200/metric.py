@@ -51,3 +51,66 @@ class Acc(object):
     def reset_metric(self):
         if self._counts is not None:
             self._counts.zero_()
+
+
+def _eval_accumulate(output, target, counts=None, class_counts=None, loss_sum=None, pred=None):
+    """kws_eval_accumulate on the current stream of `output`'s device."""
+    if not output.is_cuda:
+        raise _native.NativeError("evaluation statistics are counted on the GPU; got a CPU tensor")
+    lib = _native.load()
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None   # noqa: E731
+    with torch.cuda.device(output.device):
+        _native.check(lib.kws_eval_accumulate(
+            ptr(output), ptr(target), output.shape[0], output.shape[1], ptr(counts), ptr(class_counts), ptr(loss_sum),
+            ptr(pred), C.c_void_p(torch.cuda.current_stream(output.device).cuda_stream)), "kws_eval_accumulate")
+
+
+@register_cls('metric.PerClassAcc')
+class PerClassAcc(object):
+    """``metric.PerClassAcc`` (/root/reference/metric/per_class_acc.py:8-55) with the counts kept on the device:
+    ``accumulate`` never synchronises (the reference does two ``.tolist()`` per batch, :19-20) and returns None
+    instead of the batch's own per-class dict (``evaluate`` ignores it, run/test.py:33); ``get_metric`` returns
+    ``{class index: correct / total}`` for the classes seen, exactly like the reference (:47-51)."""
+
+    def __init__(self):
+        self._counts = None   # device int64 [n_labels][2] = (total, correct)
+
+    def get_type(self):       # MacroMetric.get_type (metric_utils.py:33-38): re-keyed by label in collect_metrics
+        from enum import Enum
+        return Enum("MetricType", {"MACRO": "MACRO", "MICRO": "MICRO"}).MICRO
+
+    def accumulate(self, output, target):
+        assert output.shape[0] == len(target)
+        n_labels = output.shape[1]
+        if self._counts is None or self._counts.device != output.device or self._counts.shape[0] != n_labels:
+            self._counts = torch.zeros((n_labels, 2), dtype=torch.int64, device=output.device)
+        output = output.float().contiguous()
+        target = target.to(output.device, torch.int64).contiguous()
+        _eval_accumulate(output, target, class_counts=self._counts)
+
+    def all_reduce(self):
+        if self._counts is not None:
+            all_reduce_counts(self._counts)
+        return self
+
+    def get_metric(self):
+        if self._counts is None:
+            return {}
+        c = self._counts.tolist()
+        return {k: cor / tot for k, (tot, cor) in enumerate(c) if tot > 0}
+
+    def reset_metric(self):
+        self._counts = None
+
+
+@register_cls('loss_fn.ce_loss')
+def ce_loss(output, target):
+    """``loss_fn.ce_loss`` (/root/reference/loss_function.py:7-9): mean categorical cross entropy of raw logits,
+    as a 0-dim tensor on the logits' device; computed by kws_eval_accumulate (no host sync).  Inference only: the
+    result carries no autograd graph."""
+    output = output.detach().float().contiguous()
+    target = target.to(output.device, torch.int64).contiguous()
+    s = torch.zeros(1, dtype=torch.float64, device=output.device)
+    if output.shape[0] > 0:
+        _eval_accumulate(output, target, loss_sum=s)
+    return (s[0] / max(output.shape[0], 1)).float()

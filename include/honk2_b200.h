@@ -146,6 +146,16 @@ int kws_model_set_chunk(kws_model_t* m, int precision, int chunk);
 int kws_acc_accumulate(const float* logits, const int64_t* target, int64_t B, int n_labels,
                        int64_t* counts, int64_t* pred, void* stream);
 
+/* One pass over a batch of logits for the whole evaluate() bookkeeping (run/test.py:28-33), nothing leaves the device:
+ *   counts        (nullable) int64[2]:            += [correct, total]                 (metric/acc.py:14-24)
+ *   class_counts  (nullable) int64[2 * n_labels]: [2 t] += 1, [2 t + 1] += correct    (metric/per_class_acc.py:14-45)
+ *   loss_sum      (nullable) double[1]:           += sum_b (logsumexp(row_b) - row_b[target_b]), i.e. the SUM form of
+ *                                                 nn.CrossEntropyLoss (loss_function.py:7-9); divide by B for its mean
+ *   pred          (nullable) int64[B]:            argmax (first maximum, NaN wins, like torch.argmax)
+ * Targets outside [0, n_labels) count as misses in `counts` and are skipped by the other two. */
+int kws_eval_accumulate(const float* logits, const int64_t* target, int64_t B, int n_labels,
+                        int64_t* counts, int64_t* class_counts, double* loss_sum, int64_t* pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

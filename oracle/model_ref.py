@@ -80,3 +80,21 @@ def acc_counts(logits, target):
     """metric/acc.py:14-22: (correct, total) from argmax(dim=1) == target."""
     pred = torch.argmax(logits, dim=1)
     return int(torch.sum(pred == target).item()), int(len(target))
+
+
+def per_class_counts(logits, target):
+    """metric/per_class_acc.py:14-45: {class: (total, correct)} over the classes present in `target`."""
+    pred = torch.argmax(logits, dim=1).tolist()
+    out = {}
+    for guess, truth in zip(pred, target.tolist()):
+        tot, cor = out.get(truth, (0, 0))
+        out[truth] = (tot + 1, cor + (1 if guess == truth else 0))
+    return out
+
+
+def ce_loss(logits, target):
+    """loss_function.py:7-9: nn.CrossEntropyLoss()(output, target) = mean over the batch of
+    logsumexp(row) - row[target] (float64 here)."""
+    x = logits.double()
+    lse = torch.logsumexp(x, dim=1)
+    return float((lse - x[torch.arange(x.shape[0]), target]).mean())

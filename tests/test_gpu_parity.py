@@ -375,3 +375,40 @@ def test_bf16_sweep_kernel_odd_map_shapes(dev, T, F, B):
         y = m(x.to(dev)).cpu().numpy()
     assert np.isfinite(y).all()
     assert logit_err(y, ref) <= BF16_TOL, logit_err(y, ref)
+
+
+def test_eval_statistics_on_device(dev):
+    """Per-class accuracy and cross entropy counted on the device (metric/per_class_acc.py:14-55,
+    loss_function.py:7-9) against the oracle and torch's own CrossEntropyLoss; accumulation over ragged batches."""
+    from honk2_b200.metric import PerClassAcc, ce_loss
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(3001, 12, generator=g) * 4.0
+    target = torch.randint(0, 11, (3001,), generator=g)          # class 11 never occurs
+    pca = PerClassAcc()
+    for lo, hi in ((0, 1000), (1000, 1001), (1001, 3001)):
+        pca.accumulate(logits[lo:hi].to(dev), target[lo:hi].to(dev))
+    ref = model_ref.per_class_counts(logits, target)
+    got = pca.get_metric()
+    assert set(got) == set(ref) and 11 not in got
+    for k, (tot, cor) in ref.items():
+        assert got[k] == cor / tot
+    loss = ce_loss(logits.to(dev), target.to(dev))
+    assert loss.is_cuda and loss.dim() == 0
+    want = model_ref.ce_loss(logits, target)
+    assert abs(float(loss) - want) <= 1e-5 * max(1.0, abs(want))
+    assert abs(float(loss) - float(torch.nn.CrossEntropyLoss()(logits, target))) <= 1e-4
+    pca.reset_metric()
+    assert pca.get_metric() == {}
+    # reference-shaped evaluate(): loss and metrics without a host sync per batch
+    from honk2_b200.evaluate import evaluate
+    from honk2_b200.metric import Acc
+
+    class Loader(list):
+        pass
+    m, _ = gpu_model("res8", "hardened", dev)
+    feats = torch.from_numpy(mfcc_ref.compute_mfccs_batch(synth.speechlike(6, seed=2)))
+    tgt = torch.tensor([0, 1, 2, 3, 4, 5])
+    res = evaluate(dev, "test", m, Loader([(feats[:4], tgt[:4]), (feats[4:], tgt[4:])]), ce_loss,
+                   {"acc": Acc(), "per_class": PerClassAcc()}, {i: f"label{i}" for i in range(12)})
+    assert set(res) == {"loss", "metric_acc", "metric_per_class"} and np.isfinite(res["loss"])
+    assert all(k.startswith("label") for k in res["metric_per_class"])

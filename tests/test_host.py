@@ -214,3 +214,28 @@ def test_argument_errors_without_gpu(native_lib):
     out = ctypes.c_void_p()
     assert native_lib.kws_frontend_create(16000, 40, 20.0, 4000.0, 512, 160, ctypes.byref(out)) == 1
     assert b"n_fft=480" in native_lib.kws_last_error()
+
+
+def test_reference_checkpoint_loading(tmp_path):
+    """utils/workspace.py:28-70: a checkpoint dict with pickled extras and DataParallel's `module.` prefix."""
+    import torch
+    import honk2_b200
+    from honk2_b200 import load_checkpoint, strip_data_parallel_prefix
+    src = honk2_b200.build_model("res8", seed=7)
+    sd = {k: v.clone() + (0.25 if v.is_floating_point() else 0) for k, v in src.state_dict().items()}
+    ckpt = {"model_state_dict": {"module." + k: v for k, v in sd.items()}, "loss_fn": len, "metrics": {"acc": object},
+            "optimizer_state_dict": {"state": {}}, "lr_scheduler_state_dict": {}, "epoch": 17}
+    path = tmp_path / "best_model.pt"
+    torch.save(ckpt, path)
+    dst = honk2_b200.build_model("res8", seed=1)
+    rest = load_checkpoint(dst, str(path))
+    assert rest["epoch"] == 17 and "model_state_dict" not in rest and "optimizer_state_dict" not in rest
+    for k, v in dst.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    # bare state_dict, no prefix; a partial prefix is left alone (strict loading then fails loudly)
+    load_checkpoint(dst, dict(src.state_dict()))
+    mixed = {"module.a": 1, "b": 2}
+    assert strip_data_parallel_prefix(mixed) is mixed
+    import pytest
+    with pytest.raises(RuntimeError):
+        load_checkpoint(dst, {"model_state_dict": {"module.layers.conv_0.weight": sd["layers.conv_0.weight"]}})
