@@ -155,6 +155,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ uint4 ld_hint(const uint4* ptr, uint64_t pol) {
   uint4 v;
   asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
@@ -1440,7 +1445,6 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
     q.out_b = p->out_b;
     q.P = P; q.Q = Q;
     q.n_layers = n; q.C = c.n_maps; q.n_labels = c.n_labels; q.T = T; q.F = F;
-    q.ph = 1; q.pw = 1;
     q.H = H; q.W = W; q.n_strips = f.n_strips;
     q.smem_c0w_off = f.c0w_off;
     {
@@ -1455,10 +1459,6 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
     {
       const char* e = std::getenv("HONK2_TC_L2POLICY");
       q.l2_policy = e ? std::atoi(e) : 1;
-    }
-    {
-      const char* e = std::getenv("HONK2_TC_ISSUE_STYLE");
-      q.issue_style = e ? std::atoi(e) : 0;
     }
     p->sweep_smem = f.smem_total;
     p->sweep_key = key;

@@ -14,13 +14,15 @@
 // so input column w is read once and feeds all nine taps with 9 MMAs of 72 cycles (the tensor-pipe
 // rate) instead of 27 MMAs of 44.  Columns are visited run by run (w = r, r+d, r+2d, ... for every
 // residue r mod d), so consecutive steps always shift the accumulator window by exactly one block.
-// A ring wrap or a fresh (not yet zeroed) block splits the MMA into N = 96 + 48 pieces.
+// Every MMA accumulates: the epilogue zeroes a ring block right after reading it.  A window that wraps around the
+// ring is issued as two narrower MMAs (N = 96 + 48).
 //
-// Activation layout ("column planar-8"): [slot][NP][W][H][8] bf16.  A TMA box {8 ch, 128 + 2d rows, 1
-// column, NP planes} starting at row -d lands in shared memory as the K-major SWIZZLE_NONE canonical
-// layout (row pitch 16 B, plane pitch = LBO); out-of-range rows are zero-filled by the TMA unit, which
-// is exactly the reference's zero padding (resnet.py:22-24, padding = dilation).  The +-d row shift
-// of a height tap is a descriptor start-address offset.
+// Activation layout ("column planar-8"): [slot][NP][W][H][8] bf16, one slot (buffers P and Q) per CTA.  A staged
+// column is [NP planes][rows -d .. 128+d][8 ch] in shared memory = the K-major SWIZZLE_NONE canonical layout (row
+// pitch 16 B, plane pitch = LBO); rows outside the map are zero, which is exactly the reference's zero padding
+// (resnet.py:22-24, padding = dilation), and the +-d row shift of a height tap is a descriptor start-address
+// offset.  Single-strip maps (H <= 128) are staged with one cp.async.bulk of H*16 contiguous bytes per plane into a
+// slot whose pad rows were zeroed once; taller maps with 4-D TMA boxes (out-of-bounds zero fill).
 //
 // conv_0 (1 -> C, resnet.py:18) runs in the same pipeline as a pseudo-layer with ONE 16-channel chunk whose only
 // live "channels" are the bf16 high and low parts of the fp32 feature (the weight slab holds w in both positions, so
@@ -42,7 +44,7 @@ namespace kws {
 // higher ids, and the epilogue warps spend half their time polling barriers; with the issuers at the low ids
 // every instruction of the (latency-critical) issue loops waited behind those polls.
 constexpr int kSwFrontWarps = 4;
-constexpr int kSwIssuers = 3;       // issuer m issues the MMAs of height tap dh = m
+constexpr int kSwIssuers = 3;       // issuer m owns every third step (all MMAs of one input column and its commits)
 constexpr int kSwMaxStages = 12;
 constexpr int kSwMaxRing = 32;
 constexpr int kSwMaxW = 256;
@@ -59,13 +61,10 @@ constexpr int kSwBarTfull = kSwBarEmpty + 8 * kSwMaxStages;    // [kSwMaxRing]
 constexpr int kSwBarTempty = kSwBarTfull + 8 * kSwMaxRing;     // [kSwMaxRing]
 constexpr int kSwBarWfull = kSwBarTempty + 8 * kSwMaxRing;     // [2]
 constexpr int kSwBarLayer = kSwBarWfull + 16;                  // [2]  all MMAs of a layer retired
-constexpr int kSwBarConv0 = kSwBarLayer + 16;                  // [1]  conv_0 output stored
-constexpr int kSwBarCol = kSwBarConv0 + 8;                     // [2][kSwMaxW]  column stored by every epilogue warp
+constexpr int kSwBarCol = kSwBarLayer + 16;                    // [2][kSwMaxW]  column stored by the owning epilogue warps
 constexpr int kSwTmemSlot = kSwBarCol + 8 * 2 * kSwMaxW;       // u32
-constexpr int kSwZero = kSwTmemSlot + 4;                       // u32, always 0 (see the MMA issuers)
-constexpr int kSwPool = round_up(kSwZero + 4, 128);            // [64] f32 pooled sums
-constexpr int kSwW0 = kSwPool + 256;                           // [64][12] f32 conv_0 weights
-constexpr int kSwKc = kSwW0;                                   // [1 + n_layers][CP] f32 epilogue constants (row 0 = conv_0 = zeros)
+constexpr int kSwPool = round_up(kSwTmemSlot + 4, 128);        // [64] f32 pooled sums
+constexpr int kSwKc = kSwPool + 256;                           // [1 + n_layers][CP] f32 epilogue constants (row 0 = conv_0 = zeros)
 constexpr int kSwKcBytes = 7168;
 constexpr int kSwCtrlBytes = round_up(kSwKc + kSwKcBytes, 1024);
 // (epilogue warp group g = warp / 4, one warp per TMEM lane quarter, owns the blocks = g mod NKC: there are NKC groups)
@@ -89,7 +88,7 @@ struct SwParams {
   __nv_bfloat16* P;             // [n_slots][NP][W][H][8]
   __nv_bfloat16* Q;
   int64_t B;
-  int n_layers, C, n_labels, T, F, ph, pw, H, W;
+  int n_layers, C, n_labels, T, F, H, W;   // (no pooling on this path: H = T, W = F)
   int n_strips;                 // ceil(H / 128)
   int smem_c0w_off;             // conv_0 weight slabs (3 * 2 * 3*CP*16 bytes), resident for the whole kernel
   int smem_w_off[2], smem_ring_off, ring_slot_bytes, n_stages;
@@ -97,7 +96,6 @@ struct SwParams {
   int bulk_rows;                // > 0 (single-strip maps): columns are staged with 1-D bulk copies of bulk_rows = H rows per plane
                                 //   into a fixed [plane][128 + 2 dmax] slot whose pad rows stay zero; 0: TMA tensor boxes
   int dmax;                     // largest dilation of the network (bulk path: data row h sits at slot row dmax + h)
-  int issue_style;              // 0: MMA operands in uniform registers, 1: ordinary registers + R2UR (experiments)
   int diag;                     // diagnostics (wrong results!): 1 = epilogue skips math and stores, 2 = skips the skip-tensor loads
   long long* debug;             // optional cycle counters of CTA 0 (HONK2_TC_DEBUG=1)
   long long* trace;             // optional [8][kSwTraceLen] event timestamps of CTA 0 (HONK2_TC_TRACE=1, needs DEBUG)
@@ -145,7 +143,6 @@ resnet_tc_sweep_kernel(const SwParams p) {
       for (int w = 0; w < W; ++w) mbar_init(col_bar(par, w), (uint32_t)(4 * n_strips));
     fence_barrier_init();
   }
-  if (threadIdx.x == 32) *reinterpret_cast<volatile uint32_t*>(smem + kSwZero) = 0u;
   if (warp == kEpiWarps + 1) tmem_alloc(smem_u32(tmem_slot), 512);
   {   // conv_0 weight slabs -> shared memory (generic copy; the fence below publishes it to the tensor core)
     const uint4* src = reinterpret_cast<const uint4*>(p.conv0_wb);
@@ -188,8 +185,9 @@ resnet_tc_sweep_kernel(const SwParams p) {
   uint4* bufP = reinterpret_cast<uint4*>(p.P) + slot_base;
   uint4* bufQ = reinterpret_cast<uint4*>(p.Q) + slot_base;
   const bool use_pol = p.l2_policy != 0;
-  const uint64_t pol_keep = l2_policy_evict_last();
-  const uint64_t pol_stream = l2_policy_evict_first();
+  // l2_policy: 1 = P evict_last / Q evict_first (default), 2 = P evict_last / Q evict_normal, 3 = P normal / Q evict_first
+  const uint64_t pol_keep = p.l2_policy == 3 ? l2_policy_evict_normal() : l2_policy_evict_last();
+  const uint64_t pol_stream = p.l2_policy == 2 ? l2_policy_evict_normal() : l2_policy_evict_first();
 
   auto layer_dil = [&](int l) { return p.use_dilation ? (1 << (l / 3)) : 1; };
   // rows per plane of a staged column = plane pitch in shared memory (kept a multiple of 8 rows = 128 B)
@@ -357,7 +355,6 @@ resnet_tc_sweep_kernel(const SwParams p) {
     // one elected lane issues the MMAs, commits and arrivals.
     const bool leader = elect_one();
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    constexpr uint32_t nz = 0u;
     if (n_seq > 0) {
       int stage = 0;
       uint32_t sphase = 0;
@@ -389,7 +386,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
           const int cur = (int)(sq & 1);
           const uint32_t plane16 = (uint32_t)box_rows;                       // plane pitch in 16-byte units
           const uint32_t a_lbo = (plane16 & 0x3FFFu) << 16;
-          const uint32_t w16 = ((sbase + (is_c0 ? p.smem_c0w_off : p.smem_w_off[wq & 1])) >> 4) + nz;
+          const uint32_t w16 = ((sbase + (is_c0 ? p.smem_c0w_off : p.smem_w_off[wq & 1])) >> 4);
           const uint32_t row0 = (uint32_t)row0_of(d);
           stamp(dbg_other);
           if (!is_c0) mbar_wait_lean(wfull_bar((int)(wq & 1)), (uint32_t)((wq >> 1) & 1));
@@ -421,7 +418,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   if constexpr (DBG) { if (is_c0 && s == 0 && r == 0 && i < kSwIssuers) stamp(dbg_utt); else stamp(dbg_full); }
                   // All operands of the step are computed BEFORE the burst, and the burst is straight-line code
                   // without predicated-off MMAs (separate path for the wrapped window).
-                  const uint32_t a16 = ((sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes) >> 4) + row0 + nz;
+                  const uint32_t a16 = ((sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes) >> 4) + row0;
                   const uint32_t d1 = tmem_u + (uint32_t)(p0 * CP);
                   const uint32_t id1 = idesc0 + (uint32_t)wrap_at * idesc_blk;
                   uint32_t al[3 * NKC], bl[3 * NKC];
