@@ -61,7 +61,8 @@ constexpr int kSwBarTfull = kSwBarEmpty + 8 * kSwMaxStages;    // [kSwMaxRing]
 constexpr int kSwBarTempty = kSwBarTfull + 8 * kSwMaxRing;     // [kSwMaxRing]
 constexpr int kSwBarWfull = kSwBarTempty + 8 * kSwMaxRing;     // [2]
 constexpr int kSwBarLayer = kSwBarWfull + 16;                  // [2]  all MMAs of a layer retired
-constexpr int kSwBarCol = kSwBarLayer + 16;                    // [2][kSwMaxW]  column stored by the owning epilogue warps
+constexpr int kSwBarTurn = kSwBarLayer + 16;                   // [kSwIssuers]  the issuers' burst token
+constexpr int kSwBarCol = kSwBarTurn + 8 * 4;                  // [2][kSwMaxW]  column stored by the owning epilogue warps
 constexpr int kSwTmemSlot = kSwBarCol + 8 * 2 * kSwMaxW;       // u32
 constexpr int kSwPool = round_up(kSwTmemSlot + 4, 128);        // [64] f32 pooled sums
 constexpr int kSwKc = kSwPool + 256;                           // [1 + n_layers][CP] f32 epilogue constants (row 0 = conv_0 = zeros)
@@ -122,6 +123,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
   auto tempty_bar = [&](int a) { return sbase + kSwBarTempty + 8u * a; };
   auto wfull_bar = [&](int i) { return sbase + kSwBarWfull + 8u * i; };
   auto layer_bar = [&](int i) { return sbase + kSwBarLayer + 8u * i; };
+  auto turn_bar = [&](int i) { return sbase + kSwBarTurn + 8u * i; };
   auto col_bar = [&](int par, int w) { return sbase + kSwBarCol + 8u * (par * kSwMaxW + w); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSwTmemSlot);
   float* s_pool = reinterpret_cast<float*>(smem + kSwPool);
@@ -139,9 +141,11 @@ resnet_tc_sweep_kernel(const SwParams p) {
     for (int s = 0; s < p.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NB; ++a) { mbar_init(tfull_bar(a), kSwIssuers); mbar_init(tempty_bar(a), 4); }
     for (int i = 0; i < 2; ++i) { mbar_init(wfull_bar(i), 1); mbar_init(layer_bar(i), kSwIssuers); }
+    for (int i = 0; i < kSwIssuers; ++i) mbar_init(turn_bar(i), 1);
     for (int par = 0; par < 2; ++par)
       for (int w = 0; w < W; ++w) mbar_init(col_bar(par, w), (uint32_t)(4 * n_strips));
     fence_barrier_init();
+    mbar_arrive(turn_bar(0));   // issuer 0 holds the burst token first
   }
   if (warp == kEpiWarps + 1) tmem_alloc(smem_u32(tmem_slot), 512);
   {   // conv_0 weight slabs -> shared memory (generic copy; the fence below publishes it to the tensor core)
@@ -359,6 +363,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
       int stage = 0;
       uint32_t sphase = 0;
       int owner = 0;            // issuer of the current step (global step counter mod 3)
+      uint32_t turn_par = 0;    // parity of this issuer's next token
       int sl = 0;               // ring slot of the output block of the CURRENT step's own column
       uint32_t pr = 0;          // use parity of that slot
       constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
@@ -429,6 +434,13 @@ resnet_tc_sweep_kernel(const SwParams p) {
                       al[kc * 3 + dh] = ((a16 + (uint32_t)(2 * kc) * plane16 + (uint32_t)(dh * d)) & 0x3FFFu) | a_lbo;
                       bl[kc * 3 + dh] = ((w16 + (uint32_t)(((kc * 3 + dh) * W_SLAB) >> 4) + (uint32_t)blk0 * blk16) & 0x3FFFu) | b_lbo;
                     }
+                  // The burst token: bursts are issued one issuer at a time, in step order.  Without it the three
+                  // issuers' bursts interleave MMA by MMA in the (blocking, shallow) issue queue, all three finish
+                  // together, then all three do their commits / bookkeeping / operand preparation at the same time and
+                  // the tensor pipe idles ~600 cycles per round (event trace).  With it, everything above this line
+                  // and the commits below overlap the other two issuers' bursts.
+                  mbar_wait_lean(turn_bar(me), turn_par);
+                  turn_par ^= 1u;
                   if (!leader) {
                     // (only the elected lane issues)
                   } else if (is_c0) {
@@ -459,6 +471,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                     }
                   }
                   if (leader) {
+                  mbar_arrive(turn_bar(me + 1 == kSwIssuers ? 0 : me + 1));   // burst issued: the next issuer's turn
                   umma_commit(empty_bar(stage));   // stage reusable once these MMAs retire
                   // this issuer's share of every block of the window; the run's edge blocks have only two
                   // contributing steps, so the issuer of the edge step stands in for the missing third
