@@ -1338,7 +1338,7 @@ static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat
 struct TcSweepPlan {
   bool ok = false;
   int n_slots = 0, n_strips = 0, smem_total = 0, n_stages = 0;
-  int c0w_off = 0, w_off[2] = {0, 0}, ring_off = 0, slot_bytes = 0;
+  int c0w_off = 0, w_off[2] = {0, 0}, skip_off = 0, ring_off = 0, slot_bytes = 0;
   std::vector<int> dil;
 };
 
@@ -1367,7 +1367,8 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W) {
   f.c0w_off = kSwCtrlBytes;
   f.w_off[0] = f.c0w_off + round_up(3 * 2 * 3 * p->CP * 16, 128);
   f.w_off[1] = f.w_off[0] + round_up(w_bytes, 128);
-  f.ring_off = round_up(f.w_off[1] + w_bytes, 1024);
+  f.skip_off = round_up(f.w_off[1] + w_bytes, 1024);
+  f.ring_off = f.skip_off + p->NKC * p->NP * 2048;   // one skip slot per epilogue warp group
   f.slot_bytes = round_up(p->NP * ((128 + 2 * dmax + 7) & ~7) * 16, 128);
   static const int max_stages = [] { const char* e = std::getenv("HONK2_TC_SWEEP_STAGES"); return e ? std::atoi(e) : kSwMaxStages; }();
   f.n_stages = std::min(std::min(kSwMaxStages, max_stages), (227 * 1024 - f.ring_off) / f.slot_bytes);
@@ -1447,6 +1448,7 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
     q.n_layers = n; q.C = c.n_maps; q.n_labels = c.n_labels; q.T = T; q.F = F;
     q.H = H; q.W = W; q.n_strips = f.n_strips;
     q.smem_c0w_off = f.c0w_off;
+    q.smem_skip_off = f.skip_off;
     {
       static const bool bulk_on = [] { const char* e = std::getenv("HONK2_TC_SWEEP_BULK"); return e == nullptr || std::atoi(e) != 0; }();
       int dmax = 1;

@@ -62,7 +62,9 @@ constexpr int kSwBarTempty = kSwBarTfull + 8 * kSwMaxRing;     // [kSwMaxRing]
 constexpr int kSwBarWfull = kSwBarTempty + 8 * kSwMaxRing;     // [2]
 constexpr int kSwBarLayer = kSwBarWfull + 16;                  // [2]  all MMAs of a layer retired
 constexpr int kSwBarTurn = kSwBarLayer + 16;                   // [kSwIssuers]  the issuers' burst token
-constexpr int kSwBarCol = kSwBarTurn + 8 * 4;                  // [2][kSwMaxW]  column stored by the owning epilogue warps
+constexpr int kSwSkipSlots = 4;     // skip-tensor staging (shared memory): one slot per epilogue warp group (<= 4 groups), [NP][128 rows][8]
+constexpr int kSwBarSkFull = kSwBarTurn + 8 * 4;               // [kSwSkipSlots]
+constexpr int kSwBarCol = kSwBarSkFull + 8 * kSwSkipSlots;     // [2][kSwMaxW]  column stored by the owning epilogue warps
 constexpr int kSwTmemSlot = kSwBarCol + 8 * 2 * kSwMaxW;       // u32
 constexpr int kSwPool = round_up(kSwTmemSlot + 4, 128);        // [64] f32 pooled sums
 constexpr int kSwKc = kSwPool + 256;                           // [1 + n_layers][CP] f32 epilogue constants (row 0 = conv_0 = zeros)
@@ -93,6 +95,7 @@ struct SwParams {
   int n_strips;                 // ceil(H / 128)
   int smem_c0w_off;             // conv_0 weight slabs (3 * 2 * 3*CP*16 bytes), resident for the whole kernel
   int smem_w_off[2], smem_ring_off, ring_slot_bytes, n_stages;
+  int smem_skip_off;            // skip staging: one slot of NP * 2048 bytes per epilogue warp group
   int l2_policy;
   int bulk_rows;                // > 0 (single-strip maps): columns are staged with 1-D bulk copies of bulk_rows = H rows per plane
                                 //   into a fixed [plane][128 + 2 dmax] slot whose pad rows stay zero; 0: TMA tensor boxes
@@ -124,6 +127,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
   auto wfull_bar = [&](int i) { return sbase + kSwBarWfull + 8u * i; };
   auto layer_bar = [&](int i) { return sbase + kSwBarLayer + 8u * i; };
   auto turn_bar = [&](int i) { return sbase + kSwBarTurn + 8u * i; };
+  auto skfull_bar = [&](int i) { return sbase + kSwBarSkFull + 8u * i; };
+  constexpr uint32_t SKIP_SLOT = NP * 128 * 16;   // bytes
   auto col_bar = [&](int par, int w) { return sbase + kSwBarCol + 8u * (par * kSwMaxW + w); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSwTmemSlot);
   float* s_pool = reinterpret_cast<float*>(smem + kSwPool);
@@ -142,6 +147,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
     for (int a = 0; a < NB; ++a) { mbar_init(tfull_bar(a), kSwIssuers); mbar_init(tempty_bar(a), 4); }
     for (int i = 0; i < 2; ++i) { mbar_init(wfull_bar(i), 1); mbar_init(layer_bar(i), kSwIssuers); }
     for (int i = 0; i < kSwIssuers; ++i) mbar_init(turn_bar(i), 1);
+    for (int i = 0; i < kSwSkipSlots; ++i) mbar_init(skfull_bar(i), 1);
     for (int par = 0; par < 2; ++par)
       for (int w = 0; w < W; ++w) mbar_init(col_bar(par, w), (uint32_t)(4 * n_strips));
     fence_barrier_init();
@@ -521,6 +527,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
     int esl = 0;         // ring slot of the block the iterator stands on
     uint32_t epr = 0;    // its use parity
     int eown = 0;        // which group owns it
+    uint32_t eskpar = 0; // parity of this group's skip slot (one use per own block of a skip layer)
     int64_t sq = 0;      // pseudo-layer counter (see the producer)
     // cycle accounting of epilogue warp 0 of CTA 0 (HONK2_TC_DEBUG=1)
     const bool edbg = DBG && p.debug != nullptr && blockIdx.x == 0 && warp == 0;
@@ -541,7 +548,6 @@ resnet_tc_sweep_kernel(const SwParams p) {
         auto layer_body = [&](auto skip_c, auto last_c) {
           constexpr bool HAS_SKIP = decltype(skip_c)::value;   // odd l: adds the skip tensor from P, stores to P in place
           constexpr bool LAST = decltype(last_c)::value;       // pooled instead of stored
-          const uint4* skip_in = bufP;
           const bool to_p = HAS_SKIP || is_c0;   // conv_0 and the skip layers write P, the others Q
           uint4* y_out = to_p ? bufP : bufQ;
           const uint64_t pol_out = to_p ? pol_keep : pol_stream;
@@ -567,15 +573,15 @@ resnet_tc_sweep_kernel(const SwParams p) {
           };
           // block iterator over (strip, run, output column of the run); every warp walks all blocks, works on its own
           struct It { int s, r, o, Lr, w; bool done; };
-          struct Own { int off, w, slot; uint32_t par; bool exists; };   // off: this lane's position inside a plane, -1 outside the map
+          struct Own { int off, w, s, slot; uint32_t par; bool exists; };   // off: this lane's position inside a plane, -1 outside the map
           It it; it.s = 0; it.r = 0; it.o = 0; it.Lr = (W + d - 1) / d; it.w = 0; it.done = false;
           auto next_own = [&]() {   // advance to this group's next block (consuming it) and describe it
-            Own ob; ob.exists = false; ob.off = -1; ob.w = 0; ob.slot = 0; ob.par = 0;
+            Own ob; ob.exists = false; ob.off = -1; ob.w = 0; ob.s = 0; ob.slot = 0; ob.par = 0;
             while (!it.done) {
               const bool mine = eown == g;
               if (mine) {
                 const int row = it.s * 128 + q * 32 + lane;
-                ob.exists = true; ob.w = it.w; ob.slot = esl; ob.par = epr;
+                ob.exists = true; ob.w = it.w; ob.s = it.s; ob.slot = esl; ob.par = epr;
                 ob.off = row < H ? it.w * H + row : -1;
               }
               // step the iterator, the ring slot and the owner
@@ -592,17 +598,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
             }
             return ob;
           };
-          auto load_skip = [&](uint4 (&pv)[NP], const Own& ob) {
-            if constexpr (HAS_SKIP) {
-              if (ob.off >= 0 && !(DBG && (p.diag & 2))) {
-#pragma unroll
-                for (int pl = 0; pl < NP; ++pl)
-                  pv[pl] = use_pol ? ld_cg_hint(skip_in + (int64_t)pl * plane_stride + ob.off, pol_keep)
-                                   : ld_cg(skip_in + (int64_t)pl * plane_stride + ob.off);   // (stored by another warp: L2, not L1)
-              }
-            }
-          };
-          auto process = [&](const Own& ob, const uint4 (&pv)[NP]) {
+          auto process = [&](const Own& ob) {
             const bool valid = ob.off >= 0;
             mbar_wait_sleepy(tfull_bar(ob.slot), ob.par);
             tc_fence_after();
@@ -611,13 +607,19 @@ resnet_tc_sweep_kernel(const SwParams p) {
             if (pending_w >= 0) { publish(pending_w); pending_w = -1; }
             if (edbg) { const long long t = clock64(); e_pub += t - e_t; e_t = t; }
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ob.slot * CP);
+            // this lane's row of the staged skip column: [plane][128 rows][16 B]
+            const uint32_t sk_addr = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT + (uint32_t)(q * 32 + lane) * 16u;
+            if constexpr (HAS_SKIP) { mbar_wait_sleepy(skfull_bar(g), eskpar); eskpar ^= 1u; }
+            // two accumulator register sets: the TMEM load of the next 16 channels is in flight during the math of these
+            uint32_t v[2][16];
+            tmem_ld16(tbase, v[0]);
 #pragma unroll
             for (int jj = 0; jj < NKC; ++jj) {
-              uint32_t v[16];
-              tmem_ld16(tbase + 16 * jj, v);
               tmem_ld_wait();
               tmem_st16_zero(tbase + 16 * jj);   // the next user of this ring slot accumulates from zero
-              if (jj == NKC - 1) {
+              if (jj + 1 < NKC) {
+                tmem_ld16(tbase + 16 * (jj + 1), v[(jj + 1) & 1]);
+              } else {
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -630,9 +632,12 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(kc8[0]), "=f"(kc8[1]), "=f"(kc8[2]), "=f"(kc8[3]) : "r"(kc_addr + (uint32_t)(64 * jj + 32 * hf)));
                   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(kc8[4]), "=f"(kc8[5]), "=f"(kc8[6]), "=f"(kc8[7]) : "r"(kc_addr + (uint32_t)(64 * jj + 32 * hf + 16)));
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[8 * hf + e]), 0.f) + kc8[e];
+                  for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[jj & 1][8 * hf + e]), 0.f) + kc8[e];
                   if constexpr (HAS_SKIP) {
-                    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&pv[2 * jj + hf]);
+                    uint4 sv;   // 8 channels of the skip tensor at this position (plane 2 jj + hf)
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sv.x), "=r"(sv.y), "=r"(sv.z), "=r"(sv.w)
+                                 : "r"(sk_addr + (uint32_t)(2 * jj + hf) * 2048u));
+                    const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&sv);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                       const float2 f = __bfloat1622float2(pb[e]);
@@ -662,13 +667,30 @@ resnet_tc_sweep_kernel(const SwParams p) {
             }
             pending_w = ob.w;
           };
-          uint4 pv[NP];
+          // Skip layers (odd l, resnet.py:51-53): the block of output column w adds column w of P.  That column is staged
+          // in this group's shared-memory slot by NP bulk copies issued by the group's quarter-0 warp as soon as all four
+          // warps have finished reading the previous one, i.e. two block periods before it is needed: no L2 latency on
+          // the epilogue's critical path and no prefetch registers (they hold a second accumulator set instead).
+          auto stage_skip = [&](const Own& ob) {
+            if constexpr (HAS_SKIP) {
+              asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");   // the group's four warps are done with the slot
+              if (q == 0 && ob.exists && elect_one()) {
+                const int rows = H - ob.s * 128 < 128 ? H - ob.s * 128 : 128;
+                mbar_expect_tx(skfull_bar(g), (uint32_t)(NP * rows * 16));
+                const uint4* src = bufP + (int64_t)ob.w * H + ob.s * 128;
+                const uint32_t d0 = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT;
+#pragma unroll
+                for (int pl = 0; pl < NP; ++pl)
+                  bulk_load_hint(d0 + (uint32_t)pl * 2048u, src + (int64_t)pl * plane_stride, (uint32_t)(rows * 16), skfull_bar(g), pol_keep);
+              }
+            }
+          };
           Own ob = next_own();
-          load_skip(pv, ob);
+          stage_skip(ob);
           while (ob.exists) {
-            process(ob, pv);
+            process(ob);
             ob = next_own();
-            load_skip(pv, ob);   // the next own block is three blocks away: two block periods of prefetch distance
+            stage_skip(ob);
           }
           if (pending_w >= 0) publish(pending_w);
           if constexpr (LAST) {
