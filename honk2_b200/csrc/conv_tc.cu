@@ -90,10 +90,17 @@ __device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) 
 }
 // Wait with few instructions per poll (for the MMA issuers, whose instruction count is the bottleneck): the
 // hardware suspends the thread until the phase completes or the hint elapses; the watchdog is read every 256 polls.
+// The hinted try_wait compiles to TRYWAIT + NANOSLEEP.SYNCS: the thread leaves the issue slots to other warps, but waking
+// up is slow; waits that are usually short poll a few times first (HONK2_TC_WAIT_POLLS, default 48; measured +2-4 %).
+__device__ int g_wait_polls;
 __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+  const int polls = g_wait_polls;
+#pragma unroll 1
+  for (int i = 0; i < polls; ++i)
+    if (mbar_try_wait(bar, parity)) return;
   long long t0 = 0;
-  for (uint32_t it = 1; !mbar_try_wait_hint(bar, parity, 100000u); ++it) {
+  for (uint32_t it = 1; !mbar_try_wait_hint(bar, parity, polls > 0 ? 1000u : 100000u); ++it) {
     if ((it & 255u) == 0u) {
       if (t0 == 0) t0 = clock64();
       else if (clock64() - t0 > kSpinLimitCycles) __trap();
@@ -1478,6 +1485,11 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
     prm.debug = dbg_buf;
   }
   if (dbg_on) { const char* e = std::getenv("HONK2_TC_DIAG"); prm.diag = e ? std::atoi(e) : 0; }
+  {
+    static const int polls = [] { const char* e = std::getenv("HONK2_TC_WAIT_POLLS"); return e ? std::atoi(e) : 48; }();
+    static bool polls_set = false;
+    if (!polls_set) { cudaMemcpyToSymbol(g_wait_polls, &polls, sizeof(int)); polls_set = true; }
+  }
   static const bool trace_on = [] { const char* e = std::getenv("HONK2_TC_TRACE"); return e && std::atoi(e) != 0; }();
   static long long* trace_buf = nullptr;
   if (dbg_on && trace_on) {
