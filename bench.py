@@ -134,7 +134,7 @@ def cpu_reference_step(model_name, n_utts, seed):
     audio_data_loader.py:26-29) then model(x) under no_grad (run/test.py:25-26)."""
     from honk2_b200 import synth
     from oracle import mfcc_ref, model_ref
-    waves = synth.broadband(n_utts, seed=seed)
+    waves = synth.broadband(n_utts, N=N_SAMPLES, seed=seed)
     t0 = time.perf_counter()
     feats = torch.from_numpy(mfcc_ref.compute_mfccs_batch(waves))
     t1 = time.perf_counter()
@@ -183,8 +183,9 @@ def run_reference_arm(args):
 
 
 def workload_config(args, batch):
-    return {"workload": f"{args.model} inference, {batch} synthetic 1 s / 16 kHz clips per GPU per step, "
-                        f"waveform -> 101x40 MFCC -> logits (12 GSC classes), random-init weights (seed of the config)",
+    secs, frames = N_SAMPLES / 16000.0, 1 + N_SAMPLES // 160
+    return {"workload": f"{args.model} inference, {batch} synthetic {secs:g} s / 16 kHz clips per GPU per step, "
+                        f"waveform -> {frames}x40 MFCC -> logits (12 GSC classes), random-init weights (seed of the config)",
             "model_config": args.model, "batch_per_gpu": batch, "clip_samples": N_SAMPLES,
             "l2": "inputs larger than L2 (512 KB.. per step: %.0f MB of waveforms per GPU)" % (batch * N_SAMPLES * 4 / 1e6)}
 
@@ -198,6 +199,8 @@ def main():
     ap.add_argument("--model", default="res15")
     ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--clip-samples", type=int, default=16000,
+                    help="samples per clip (16000 = the headline 1 s clips; 144000 = the hey_snips-shaped 9 s clips of config 5)")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0, help="concurrent chunk streams of the bf16 path (0 = library default)")
     ap.add_argument("--ref-batch", type=int, default=64)
@@ -206,6 +209,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    global N_SAMPLES
+    N_SAMPLES = args.clip_samples
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -240,7 +245,7 @@ def main():
 
     # synthetic data: a few distinct batches (each 524 MB > L2), device resident for `value`
     n_sets = 2
-    host_sets = [torch.from_numpy(synth.broadband(B, seed=100 * rank + s)).pin_memory() for s in range(n_sets)]
+    host_sets = [torch.from_numpy(synth.broadband(B, N=N_SAMPLES, seed=100 * rank + s)).pin_memory() for s in range(n_sets)]
     dev_sets = [h.to(dev) for h in host_sets]
     targets = torch.randint(0, model.n_labels, (B,), device=dev)
     acc = Acc()
