@@ -1461,7 +1461,7 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
       int dmax = 1;
       for (int dd : f.dil) dmax = std::max(dmax, dd);
       q.dmax = dmax;
-      q.bulk_rows = (bulk_on && f.n_strips == 1) ? H : 0;
+      q.bulk_rows = bulk_on ? H : 0;
     }
     q.smem_w_off[0] = f.w_off[0]; q.smem_w_off[1] = f.w_off[1];
     q.smem_ring_off = f.ring_off; q.ring_slot_bytes = f.slot_bytes; q.n_stages = f.n_stages;

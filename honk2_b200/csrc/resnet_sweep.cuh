@@ -97,8 +97,10 @@ struct SwParams {
   int smem_w_off[2], smem_ring_off, ring_slot_bytes, n_stages;
   int smem_skip_off;            // skip staging: one slot of NP * 2048 bytes per epilogue warp group
   int l2_policy;
-  int bulk_rows;                // > 0 (single-strip maps): columns are staged with 1-D bulk copies of bulk_rows = H rows per plane
-                                //   into a fixed [plane][128 + 2 dmax] slot whose pad rows stay zero; 0: TMA tensor boxes
+  int bulk_rows;                // != 0: columns are staged with one 1-D bulk copy per plane (the rows of the strip's window
+                                //   that lie inside the map) into a fixed [plane][128 + 2 dmax] slot; pad rows are zero
+                                //   (single strip: zeroed once and never written; several strips: re-zeroed by the producer
+                                //   for the strips that touch the map's top / bottom).  0: TMA tensor boxes
   int dmax;                     // largest dilation of the network (bulk path: data row h sits at slot row dmax + h)
   int diag;                     // diagnostics (wrong results!): 1 = epilogue skips math and stores, 2 = skips the skip-tensor loads
   long long* debug;             // optional cycle counters of CTA 0 (HONK2_TC_DEBUG=1)
@@ -309,11 +311,27 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   // 32-byte sector per row: 2.6x the bytes, measured with ncu)
                   // (issued by ONE lane with warp-uniform operands: per-lane operands would make the compiler wrap every
                   // copy in a 15-instruction ELECT / R2UR loop, and this warp's instruction count is what bounds it)
-                  const uint32_t bytes = (uint32_t)p.bulk_rows * 16u;
+                  const int win_lo = s * 128 - d, win_hi = s * 128 + 128 + d;         // rows the MMAs of this strip read
+                  const int h_lo = win_lo > 0 ? win_lo : 0, h_hi = win_hi < H ? win_hi : H;
+                  if (n_strips > 1 && (win_lo < 0 || win_hi > H)) {
+                    // this slot last held an interior strip (data in every row): restore the zero rows of the padding
+                    unsigned char* slot = smem + p.smem_ring_off + (size_t)stage * p.ring_slot_bytes;
+                    const int top = win_lo < 0 ? -win_lo : 0;                       // rows above the map
+                    const int bot = win_hi > H ? win_hi - H : 0;                    // rows below the map
+                    const int r_top = p.dmax - d, r_bot = p.dmax + H - s * 128;     // their first slot rows
+                    for (int i = lane; i < NP * (top + bot); i += 32) {
+                      const int pl = i / (top + bot), k = i - pl * (top + bot);
+                      const int row = k < top ? r_top + k : r_bot + (k - top);
+                      *reinterpret_cast<uint4*>(slot + (size_t)(pl * box_rows + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                  }
+                  const uint32_t bytes = (uint32_t)(h_hi - h_lo) * 16u;
                   if (leader) {
                     mbar_expect_tx(full_bar(stage), bytes * NP);
-                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)w * H;
-                    const uint32_t d0 = dst + (uint32_t)p.dmax * 16u;
+                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)w * H + h_lo;
+                    const uint32_t d0 = dst + (uint32_t)(p.dmax + h_lo - s * 128) * 16u;
 #pragma unroll
                     for (int pl = 0; pl < NP; ++pl)
                       bulk_load_hint(d0 + (uint32_t)(pl * box_rows) * 16u, src + (int64_t)pl * plane_stride, bytes, full_bar(stage), pol);
