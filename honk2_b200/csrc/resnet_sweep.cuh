@@ -229,7 +229,6 @@ resnet_tc_sweep_kernel(const SwParams p) {
       }
       for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
         const float* feat_b = p.feat + b * (int64_t)p.T * p.F;
-        float4 c0_f[5];   // conv_0: this lane's rows of the current group of four feature columns
         const bool c0_vec = (p.F & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feat) & 15) == 0;
         for (int ll = 0; ll < nl1; ++ll, ++sq) {
           const bool is_c0 = ll == 0;
@@ -258,6 +257,82 @@ resnet_tc_sweep_kernel(const SwParams p) {
           };
           const int prev_par = (int)((sq - 1) & 1);
           const uint32_t prev_phase = (uint32_t)(((sq - 1) >> 1) & 1);
+          if (is_c0) {
+            // conv_0 pseudo-layer: the producer BUILDS the staged columns.  Rows 128 s - 1 .. 128 s + 128 of feature
+            // column w, each as {hi, lo, 0 x 6} bf16 (fp32 feature split into two bf16 parts) in plane 0; the MMA's
+            // second K half reads the same plane (LBO = 0) against zero weights, so nothing an earlier layer left in
+            // the slot can reach this utterance.  Zero outside the map = the reference's padding.  Up to four
+            // consecutive columns are built per pass from one 16-byte feature load per row: the MMAs of a conv_0 step
+            // are few, so this warp's instruction count is what bounds the pseudo-layer.
+            const int r0 = row0_of(1);
+            // the NEXT utterance's features into L2 now, a whole utterance period before they are needed: the column
+            // builder's loads otherwise wait for DRAM once per pass
+            if (b + gridDim.x < p.B) {
+              const char* nf = reinterpret_cast<const char*>(p.feat + (b + gridDim.x) * (int64_t)p.T * p.F);
+              const int n_lines = (p.T * p.F * 4 + 127) >> 7;
+              for (int i = lane; i < n_lines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nf + (size_t)i * 128));
+            }
+            for (int s = 0; s < n_strips; ++s)
+              for (int w0 = 0; w0 < W; w0 += 4) {
+                const int cnt = c0_vec ? (W - w0 < 4 ? W - w0 : 4) : 1;
+                for (int w = w0; w < (W < w0 + 4 ? W : w0 + 4); w += cnt) {
+                  pstamp(pd_issue);
+                  // the stages of these `cnt` steps
+                  int st[4]; uint32_t ph[4];
+                  { int t = stage; uint32_t q2 = sphase;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { st[c] = t; ph[c] = q2; if (++t == p.n_stages) { t = 0; q2 ^= 1u; } } }
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) if (c < cnt) mbar_wait_lean(empty_bar(st[c]), ph[c] ^ 1u);
+                  pstamp(pd_empty);
+                  float4 fr[5];
+#pragma unroll
+                  for (int k = 0; k < 5; ++k) {   // all loads first
+                    const int rr = lane + 32 * k;
+                    const int h = s * 128 - 1 + rr;
+                    fr[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rr < 130 && h >= 0 && h < p.T) {
+                      if (c0_vec) fr[k] = __ldg(reinterpret_cast<const float4*>(feat_b + (int64_t)h * p.F + w));
+                      else fr[k].x = __ldg(feat_b + (int64_t)h * p.F + w);
+                    }
+                  }
+                  pstamp(pd_col);   // (debug accounting: the feature-load latency is booked under "previous layer's column")
+#pragma unroll
+                  for (int k = 0; k < 5; ++k) {
+                    const int rr = lane + 32 * k;
+                    if (rr < 130) {
+                      const float4 f = fr[k];
+                      const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+                      for (int c = 0; c < 4; ++c) {
+                        if (c < cnt) {
+                          const __nv_bfloat16 hi = __float2bfloat16_rn(fv[c]);
+                          const __nv_bfloat16 lo = __float2bfloat16_rn(fv[c] - __bfloat162float(hi));
+                          const uint32_t packed = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+                          unsigned char* slot = smem + p.smem_ring_off + (size_t)st[c] * p.ring_slot_bytes;
+                          *reinterpret_cast<uint4*>(slot + (size_t)(r0 + rr) * 16) = make_uint4(packed, 0u, 0u, 0u);
+                        }
+                      }
+                    }
+                  }
+                  fence_async_smem();   // generic-proxy writes -> visible to the tensor core
+                  __syncwarp();
+                  if (leader) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (c < cnt) mbar_arrive(full_bar(st[c]));
+                  }
+                  for (int c = 0; c < cnt; ++c) {
+                    if constexpr (DBG) {
+                      if (ptrace && leader && pstep < kSwTraceLen) p.trace[0 * kSwTraceLen + pstep] = clock64();
+                      ++pstep;
+                    }
+                    if (++stage == p.n_stages) { stage = 0; sphase ^= 1; }
+                  }
+                  pstamp(pd_c0);
+                }
+              }
+            continue;   // (conv_0 has no weights to request and does not advance the real-layer counter)
+          }
           int step = 0;
           for (int s = 0; s < n_strips; ++s)
             for (int r = 0; r < n_runs; ++r)
@@ -269,44 +344,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 mbar_wait_lean(empty_bar(stage), sphase ^ 1);
                 pstamp(pd_empty);
                 const uint32_t dst = sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes;
-                if (is_c0) {
-                  // conv_0 column: rows 128 s - 1 .. 128 s + 128 of feature column w, each as {hi, lo, 0 x 6} bf16 in
-                  // plane 0 and zeros in plane 1 (written, not assumed: whatever an earlier layer left there must not
-                  // reach this utterance, 0 x NaN = NaN); zero outside the map = the reference's padding
-                  unsigned char* slot = smem + p.smem_ring_off + (size_t)stage * p.ring_slot_bytes;
-                  const int r0 = row0_of(1);
-                  // the features of four consecutive columns are fetched together (one 16-byte load per row), so only
-                  // every fourth column pays the L2 latency
-                  if ((w & 3) == 0 || !c0_vec) {
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                      const int h = s * 128 - 1 + lane + 32 * k;
-                      const bool ok = lane + 32 * k < 130 && h >= 0 && h < p.T;
-                      if (c0_vec) {
-                        c0_f[k] = ok ? __ldg(reinterpret_cast<const float4*>(feat_b + (int64_t)h * p.F + w)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                      } else {
-                        c0_f[k].x = ok ? __ldg(feat_b + (int64_t)h * p.F + w) : 0.f;
-                      }
-                    }
-                  }
-#pragma unroll
-                  for (int k = 0; k < 5; ++k) {
-                    const int rr = lane + 32 * k;
-                    if (rr < 130) {
-                      const int c = c0_vec ? (w & 3) : 0;
-                      const float v = c == 0 ? c0_f[k].x : (c == 1 ? c0_f[k].y : (c == 2 ? c0_f[k].z : c0_f[k].w));
-                      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-                      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-                      const uint32_t packed = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
-                      *reinterpret_cast<uint4*>(slot + (size_t)(r0 + rr) * 16) = make_uint4(packed, 0u, 0u, 0u);
-                      *reinterpret_cast<uint4*>(slot + (size_t)(box_rows + r0 + rr) * 16) = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                  }
-                  fence_async_smem();   // generic-proxy writes -> visible to the tensor core
-                  __syncwarp();
-                  if (leader) mbar_arrive(full_bar(stage));
-                  pstamp(pd_c0);
-                } else if (p.bulk_rows > 0) {
+                if (p.bulk_rows > 0) {
                   // one contiguous H x 16 B run per 8-channel plane (a TMA box with 16-byte rows fetches a whole
                   // 32-byte sector per row: 2.6x the bytes, measured with ncu)
                   // (issued by ONE lane with warp-uniform operands: per-lane operands would make the compiler wrap every
@@ -414,7 +452,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
           const int n_runs = d < W ? d : W;
           const int cur = (int)(sq & 1);
           const uint32_t plane16 = (uint32_t)box_rows;                       // plane pitch in 16-byte units
-          const uint32_t a_lbo = (plane16 & 0x3FFFu) << 16;
+          // (conv_0: both K halves read plane 0, the weights of the second half are zero)
+          const uint32_t a_lbo = is_c0 ? 0u : (plane16 & 0x3FFFu) << 16;
           const uint32_t w16 = ((sbase + (is_c0 ? p.smem_c0w_off : p.smem_w_off[wq & 1])) >> 4);
           const uint32_t row0 = (uint32_t)row0_of(d);
           stamp(dbg_other);
