@@ -916,6 +916,7 @@ struct TcResNet {
   int fused_smem = 0;
   // column-sweep whole-network kernel (resnet_sweep.cuh), preferred when the map is tall enough
   bool sweep_enabled = true;
+  bool sweep_packed = false;   // HONK2_TC_SWEEP_PACKED=1: whole columns contiguous in HBM (one bulk copy per step; measured slower, see tc_sweep_plan)
   void* sweep_dev = nullptr;   // [SwLayerDesc x n_layers][pad][CUtensorMap x n_layers]
   std::tuple<int, int, const void*> sweep_key{-1, -1, nullptr};
   SwParams sweep_prm{};
@@ -1071,6 +1072,7 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
     p->fused_enabled = fenv == nullptr || std::atoi(fenv) != 0;
     const char* senv = std::getenv("HONK2_TC_SWEEP");
     p->sweep_enabled = senv == nullptr || std::atoi(senv) != 0;
+    { const char* e = std::getenv("HONK2_TC_SWEEP_PACKED"); p->sweep_packed = e != nullptr && std::atoi(e) != 0; }
     const char* env = std::getenv("HONK2_TC_LANES");
     p->lanes = env ? std::max(1, std::min(kTcMaxLanes, std::atoi(env))) : 2;
     bool ok = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) == cudaSuccess;
@@ -1346,6 +1348,8 @@ struct TcSweepPlan {
   bool ok = false;
   int n_slots = 0, n_strips = 0, smem_total = 0, n_stages = 0;
   int c0w_off = 0, w_off[2] = {0, 0}, skip_off = 0, ring_off = 0, slot_bytes = 0;
+  int dmax = 1, col_rows = 0;
+  bool bulk = false, packed = false;   // staging by bulk copies; whole columns contiguous in HBM (resnet_sweep.cuh)
   std::vector<int> dil;
 };
 
@@ -1376,17 +1380,36 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W) {
   f.w_off[1] = f.w_off[0] + round_up(w_bytes, 128);
   f.skip_off = round_up(f.w_off[1] + w_bytes, 1024);
   f.ring_off = f.skip_off + p->NKC * p->NP * 2048;   // one skip slot per epilogue warp group
-  f.slot_bytes = round_up(p->NP * ((128 + 2 * dmax + 7) & ~7) * 16, 128);
+  f.dmax = dmax;
+  static const bool bulk_on = [] { const char* e = std::getenv("HONK2_TC_SWEEP_BULK"); return e == nullptr || std::atoi(e) != 0; }();
+  f.bulk = bulk_on;
+  // Packed columns (opt-in): single strip, and plane pitch H + dmax <= 128 rows so that a skip column fits its 128-row
+  // slot.  One bulk copy per step instead of NP relieves the producer warp (+7 % when probed with a same-size single
+  // copy on the planar layout), but the zero rows between planes make the activations 18 % larger (res15: 136 MB for
+  // 148 CTAs against the 126 MB L2) and the whole kernel measured 4 % SLOWER (18.6 vs 17.8 ms), so planar stays the default.
+  f.packed = bulk_on && p->sweep_packed && f.n_strips == 1 && H + dmax <= 128;
+  // planar layout: columns start on 128-byte lines (every line of a dead Q column can then be discarded from L2);
+  // the TMA-box fallback keeps the dense pitch its tensor maps describe
+  static const bool col_align = [] { const char* e = std::getenv("HONK2_TC_SWEEP_COLALIGN"); return e != nullptr && std::atoi(e) != 0; }();
+  f.col_rows = (bulk_on && col_align) ? round_up(H, 8) : H;
+  int slack = 0;
+  if (f.packed) {
+    f.slot_bytes = round_up((p->NP * (H + dmax) + dmax) * 16, 128);
+    slack = 2048;   // the 128-row MMA operand of the last plane of the last stage reaches (128 - H) rows past its slot
+  } else {
+    f.slot_bytes = round_up(p->NP * ((128 + 2 * dmax + 7) & ~7) * 16, 128);
+  }
   static const int max_stages = [] { const char* e = std::getenv("HONK2_TC_SWEEP_STAGES"); return e ? std::atoi(e) : kSwMaxStages; }();
-  f.n_stages = std::min(std::min(kSwMaxStages, max_stages), (227 * 1024 - f.ring_off) / f.slot_bytes);
+  f.n_stages = std::min(std::min(kSwMaxStages, max_stages), (227 * 1024 - slack - f.ring_off) / f.slot_bytes);
   if (f.n_stages < 3) return f;
-  f.smem_total = f.ring_off + f.n_stages * f.slot_bytes;
+  f.smem_total = f.ring_off + f.n_stages * f.slot_bytes + slack;
   f.ok = true;
   return f;
 }
 
 static size_t tc_sweep_ws_bytes(const TcResNet* p, const TcSweepPlan& f, int H, int W, size_t* buf_out) {
-  const size_t buf = round_up<size_t>((size_t)f.n_slots * p->NP * H * W * 16, 1024);
+  const size_t col_rows = f.packed ? (size_t)p->NP * (H + f.dmax) + f.dmax : (size_t)p->NP * f.col_rows;
+  const size_t buf = round_up<size_t>((size_t)f.n_slots * col_rows * W * 16, 1024);
   if (buf_out) *buf_out = buf;
   return 2 * buf;
 }
@@ -1456,12 +1479,13 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
     q.H = H; q.W = W; q.n_strips = f.n_strips;
     q.smem_c0w_off = f.c0w_off;
     q.smem_skip_off = f.skip_off;
+    q.dmax = f.dmax;
+    q.bulk_rows = f.bulk ? H : 0;
+    q.packed = f.packed ? 1 : 0;
+    q.col_rows = f.col_rows;
     {
-      static const bool bulk_on = [] { const char* e = std::getenv("HONK2_TC_SWEEP_BULK"); return e == nullptr || std::atoi(e) != 0; }();
-      int dmax = 1;
-      for (int dd : f.dil) dmax = std::max(dmax, dd);
-      q.dmax = dmax;
-      q.bulk_rows = bulk_on ? H : 0;
+      const char* e = std::getenv("HONK2_TC_SWEEP_DISCARD");
+      q.discard_q = (e ? std::atoi(e) != 0 : true) && f.n_strips == 1;
     }
     q.smem_w_off[0] = f.w_off[0]; q.smem_w_off[1] = f.w_off[1];
     q.smem_ring_off = f.ring_off; q.ring_slot_bytes = f.slot_bytes; q.n_stages = f.n_stages;

@@ -102,6 +102,9 @@ struct SwParams {
                                 //   (single strip: zeroed once and never written; several strips: re-zeroed by the producer
                                 //   for the strips that touch the map's top / bottom).  0: TMA tensor boxes
   int dmax;                     // largest dilation of the network (bulk path: data row h sits at slot row dmax + h)
+  int packed;                   // 1 = P / Q hold whole COLUMNS contiguously, [w][pad dmax | plane 0 | pad | plane 1 | ... | pad] (single strip)
+  int col_rows;                 // planar layout: rows between consecutive columns of a plane (H, or H rounded up to 8 = whole 128-byte lines)
+  int discard_q;                // 1 = Q columns are discarded from L2 (no write-back) once the layer that reads them has consumed them
   int diag;                     // diagnostics (wrong results!): 1 = epilogue skips math and stores, 2 = skips the skip-tensor loads
   long long* debug;             // optional cycle counters of CTA 0 (HONK2_TC_DEBUG=1)
   long long* trace;             // optional [8][kSwTraceLen] event timestamps of CTA 0 (HONK2_TC_TRACE=1, needs DEBUG)
@@ -143,6 +146,20 @@ resnet_tc_sweep_kernel(const SwParams p) {
   const int64_t n_seq = n_wq;
   const int nl1 = n_layers + 1;                 // pseudo-layers per utterance: conv_0, then the C -> C layers
 
+  // Activation layout in HBM (16-byte units = 8 bf16 channels of one position), one slot per CTA:
+  //   planar  [plane][w][h]                                   (multi-strip maps, TMA fallback)
+  //   packed  [w][ dmax zero rows | plane 0: H rows | dmax zero rows | plane 1 | ... | dmax zero rows ]
+  // The packed form makes a staged column ONE contiguous run: one bulk copy per step instead of NP, and the zero rows
+  // between planes (shared by the plane above and the plane below) are the convolution's height padding.
+  const bool packed = p.packed != 0;
+  const int PP = H + p.dmax;                    // packed: plane pitch (rows)
+  const int COLP = NP * PP + p.dmax;            // packed: column pitch (rows)
+  const int col_pitch = packed ? COLP : p.col_rows, col_base = packed ? p.dmax : 0;
+  const int64_t plane_stride = packed ? (int64_t)PP : (int64_t)W * col_pitch;   // 16-byte units
+  const int64_t slot_base = (int64_t)blockIdx.x * (packed ? (int64_t)W * COLP : (int64_t)NP * W * col_pitch);   // this CTA's utterance slot
+  uint4* bufP = reinterpret_cast<uint4*>(p.P) + slot_base;
+  uint4* bufQ = reinterpret_cast<uint4*>(p.Q) + slot_base;
+
   // ---- one-time setup
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.n_stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -176,6 +193,19 @@ resnet_tc_sweep_kernel(const SwParams p) {
     const int n16 = p.n_stages * (p.ring_slot_bytes >> 4);
     for (int i = threadIdx.x; i < n16; i += sw_threads(NKC)) ring[i] = make_uint4(0u, 0u, 0u, 0u);
   }
+  if (packed) {
+    // the zero rows of this CTA's slot (the workspace is scratch: nothing is assumed about its contents); the epilogue
+    // only ever stores data rows, so they stay zero for the whole launch
+    const int pad_rows = (NP + 1) * p.dmax;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < W * pad_rows; i += sw_threads(NKC)) {
+      const int w = i / pad_rows, k = i - w * pad_rows, region = k / p.dmax, rr = k - region * p.dmax;
+      const int row = region == 0 ? rr : p.dmax + (region - 1) * PP + H + rr;
+      bufP[(int64_t)w * COLP + row] = z;
+      bufQ[(int64_t)w * COLP + row] = z;
+    }
+    fence_async_global();   // read by this CTA's bulk copies (async proxy)
+  }
   fence_async_smem();   // generic-proxy writes (zeros, conv_0 weights) -> visible to the tensor core's (async proxy) reads
   tc_fence_before();
   __syncthreads();
@@ -192,10 +222,6 @@ resnet_tc_sweep_kernel(const SwParams p) {
   __syncthreads();
   tc_fence_after();
 
-  const int64_t plane_stride = (int64_t)W * H;                          // 16-byte units
-  const int64_t slot_base = (int64_t)blockIdx.x * NP * plane_stride;    // this CTA's utterance slot
-  uint4* bufP = reinterpret_cast<uint4*>(p.P) + slot_base;
-  uint4* bufQ = reinterpret_cast<uint4*>(p.Q) + slot_base;
   const bool use_pol = p.l2_policy != 0;
   // l2_policy: 1 = P evict_last / Q evict_first (default), 2 = P evict_last / Q evict_normal, 3 = P normal / Q evict_first
   const uint64_t pol_keep = p.l2_policy == 3 ? l2_policy_evict_normal() : l2_policy_evict_last();
@@ -203,7 +229,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
 
   auto layer_dil = [&](int l) { return p.use_dilation ? (1 << (l / 3)) : 1; };
   // rows per plane of a staged column = plane pitch in shared memory (kept a multiple of 8 rows = 128 B)
-  auto box_rows_of = [&](int d) { return p.bulk_rows > 0 ? 128 + 2 * p.dmax : ((128 + 2 * d + 7) & ~7); };
+  auto box_rows_of = [&](int d) { return packed ? PP : p.bulk_rows > 0 ? 128 + 2 * p.dmax : ((128 + 2 * d + 7) & ~7); };
   // slot row that the height tap dh = 0 of output row 0 reads
   auto row0_of = [&](int d) { return p.bulk_rows > 0 ? p.dmax - d : 0; };
 
@@ -344,7 +370,13 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 mbar_wait_lean(empty_bar(stage), sphase ^ 1);
                 pstamp(pd_empty);
                 const uint32_t dst = sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes;
-                if (p.bulk_rows > 0) {
+                if (packed) {
+                  // the whole column, zero rows included, in one copy
+                  if (leader) {
+                    mbar_expect_tx(full_bar(stage), (uint32_t)COLP * 16u);
+                    bulk_load_hint(dst, (in_q ? bufQ : bufP) + (int64_t)w * COLP, (uint32_t)COLP * 16u, full_bar(stage), pol);
+                  }
+                } else if (p.bulk_rows > 0) {
                   // one contiguous H x 16 B run per 8-channel plane (a TMA box with 16-byte rows fetches a whole
                   // 32-byte sector per row: 2.6x the bytes, measured with ncu)
                   // (issued by ONE lane with warp-uniform operands: per-lane operands would make the compiler wrap every
@@ -368,7 +400,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   const uint32_t bytes = (uint32_t)(h_hi - h_lo) * 16u;
                   if (leader) {
                     mbar_expect_tx(full_bar(stage), bytes * NP);
-                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)w * H + h_lo;
+                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)w * col_pitch + h_lo;
                     const uint32_t d0 = dst + (uint32_t)(p.dmax + h_lo - s * 128) * 16u;
 #pragma unroll
                     for (int pl = 0; pl < NP; ++pl)
@@ -639,7 +671,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
               if (mine) {
                 const int row = it.s * 128 + q * 32 + lane;
                 ob.exists = true; ob.w = it.w; ob.s = it.s; ob.slot = esl; ob.par = epr;
-                ob.off = row < H ? it.w * H + row : -1;
+                ob.off = row < H ? it.w * col_pitch + col_base + row : -1;
               }
               // step the iterator, the ring slot and the owner
               ++it.o; it.w += d;
@@ -666,7 +698,26 @@ resnet_tc_sweep_kernel(const SwParams p) {
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ob.slot * CP);
             // this lane's row of the staged skip column: [plane][128 rows][16 B]
             const uint32_t sk_addr = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT + (uint32_t)(q * 32 + lane) * 16u;
-            if constexpr (HAS_SKIP) { mbar_wait_sleepy(skfull_bar(g), eskpar); eskpar ^= 1u; }
+            const uint32_t sk_plane = packed ? (uint32_t)PP * 16u : 2048u;
+            if constexpr (HAS_SKIP) {
+              // This layer READS Q (the previous layer's output), one column per step, and the MMAs of this block were
+              // the last consumers of Q column w.  Nothing reads that column again before the next even layer rewrites
+              // it, so its dirty lines need not ever reach HBM: discard the 128-byte lines that lie wholly inside the
+              // column (lines shared with the neighbouring columns stay).  One line per lane, planes 16 lanes apart.
+              if (p.discard_q) {
+                const int t = q * 32 + lane, pl = t >> 4, j = t & 15;
+                if (pl < NP) {
+                  // (single strip: H <= 128 rows = at most 16 lines per plane, one per lane)
+                  const char* qb = reinterpret_cast<const char*>(bufQ);
+                  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(qb) & 127u);
+                  const uint32_t o0 = ((uint32_t)pl * (uint32_t)plane_stride + (uint32_t)(ob.w * col_pitch + col_base)) * 16u + mis;
+                  const uint32_t a = ((o0 + 127u) & ~127u) + (uint32_t)j * 128u;
+                  if (a + 128u <= o0 + (uint32_t)(packed ? H : col_pitch) * 16u)   // (rows H .. col_pitch-1 of a column are never used)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(qb + (a - mis)) : "memory");
+                }
+              }
+              mbar_wait_sleepy(skfull_bar(g), eskpar); eskpar ^= 1u;
+            }
             // two accumulator register sets: the TMEM load of the next 16 channels is in flight during the math of these
             uint32_t v[2][16];
             tmem_ld16(tbase, v[0]);
@@ -693,7 +744,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   if constexpr (HAS_SKIP) {
                     uint4 sv;   // 8 channels of the skip tensor at this position (plane 2 jj + hf)
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sv.x), "=r"(sv.y), "=r"(sv.z), "=r"(sv.w)
-                                 : "r"(sk_addr + (uint32_t)(2 * jj + hf) * 2048u));
+                                 : "r"(sk_addr + (uint32_t)(2 * jj + hf) * sk_plane));
                     const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&sv);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -731,10 +782,16 @@ resnet_tc_sweep_kernel(const SwParams p) {
           auto stage_skip = [&](const Own& ob) {
             if constexpr (HAS_SKIP) {
               asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");   // the group's four warps are done with the slot
-              if (q == 0 && ob.exists && elect_one()) {
+              if (packed) {
+                if (q == 0 && ob.exists && elect_one()) {   // planes PP rows apart, one copy (host plan: PP <= 128)
+                  const uint32_t bytes = (uint32_t)(NP * PP) * 16u;
+                  mbar_expect_tx(skfull_bar(g), bytes);
+                  bulk_load_hint(sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT, bufP + (int64_t)ob.w * COLP + p.dmax, bytes, skfull_bar(g), pol_keep);
+                }
+              } else if (q == 0 && ob.exists && elect_one()) {
                 const int rows = H - ob.s * 128 < 128 ? H - ob.s * 128 : 128;
                 mbar_expect_tx(skfull_bar(g), (uint32_t)(NP * rows * 16));
-                const uint4* src = bufP + (int64_t)ob.w * H + ob.s * 128;
+                const uint4* src = bufP + (int64_t)ob.w * col_pitch + ob.s * 128;
                 const uint32_t d0 = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT;
 #pragma unroll
                 for (int pl = 0; pl < NP; ++pl)

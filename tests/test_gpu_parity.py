@@ -330,6 +330,25 @@ def test_bf16_column_sweep_kernel_matches_position_major_kernel_at_full_batch(de
     assert logit_err(ys[0][torch.from_numpy(idx).to(dev)].cpu().numpy(), ref) <= BF16_TOL
 
 
+def test_bf16_sweep_kernel_packed_column_layout(dev, monkeypatch, model_golden):
+    """HONK2_TC_SWEEP_PACKED=1 (opt-in): activations stored as whole columns with the zero padding rows in HBM, staged
+    by one bulk copy per step.  Same arithmetic as the planar layout, so the logits must agree to accumulation-order
+    noise, and with the reference golden to the bf16 tolerance."""
+    feats = torch.from_numpy(model_golden["feats"]).to(dev)
+    with torch.no_grad():
+        monkeypatch.setenv("HONK2_TC_SWEEP_PACKED", "1")
+        m_packed, _ = gpu_model("res15", "hardened", dev, precision="bf16")
+        y_packed = m_packed(feats)
+        y_again = m_packed(feats)
+        monkeypatch.setenv("HONK2_TC_SWEEP_PACKED", "0")
+        m_planar, _ = gpu_model("res15", "hardened", dev, precision="bf16")
+        y_planar = m_planar(feats)
+    scale = float(y_planar.abs().max())
+    assert float((y_packed - y_planar).abs().max()) <= 2e-3 * scale
+    assert float((y_packed - y_again).abs().max()) <= 2e-3 * scale
+    assert logit_err(y_packed.cpu().numpy(), model_golden["res15/hardened/logits"]) <= BF16_TOL
+
+
 @pytest.mark.parametrize("name", ["res15", "res15_narrow"])
 def test_bf16_resnet_other_time_lengths(dev, name, model_golden):
     """T = 301 frames: the column-sweep kernel runs three 128-row strips per column and stages them with TMA boxes
