@@ -351,6 +351,33 @@ def main():
                "sample": f"{n} synthetic 1 s clips in batches of {args.ref_batch}: numpy compute_mfccs restatement per sample "
                          f"({fe_s:.1f} s) + PyTorch-CPU fp32 {args.model} forward ({mo_s:.1f} s)"}
 
+    # ---- streaming windows, reported next to the headline: B windows of 1 s at a 10 ms shift
+    # (gsc_dev_config.json:62-63) from one resident stream; front-end alone and front-end + network.
+    streaming = None
+    if world == 1 and N_SAMPLES == 16000:
+        with torch.no_grad():
+            stream = torch.from_numpy(synth.broadband(1, N=B * 160 + N_SAMPLES, seed=77)[0]).to(dev)
+            feats_s = torch.empty((B, fe.n_frames(N_SAMPLES), fe.n_mels), dtype=torch.float32, device=dev)
+
+            def timed(fn, reps=5):
+                for _ in range(2):
+                    fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(reps):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / reps
+
+            ms_fe_stream = timed(lambda: fe.compute_mfccs_stream(stream, N_SAMPLES, 160, out=feats_s))
+            ms_fe_batch = timed(lambda: fe.compute_mfccs_batch(dev_sets[0], out=feats_s))
+            ms_all = timed(lambda: model(fe.compute_mfccs_stream(stream, N_SAMPLES, 160, out=feats_s)))
+            streaming = {"windows_per_step": B, "window_samples": N_SAMPLES, "shift_samples": 160,
+                         "frontend_ms_shared_frames": ms_fe_stream, "frontend_ms_per_window_batch": ms_fe_batch,
+                         "windows_per_s_frontend_plus_network": B / (ms_all / 1e3)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
@@ -358,7 +385,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 4,
                     "d2h_bytes_per_step": B * model.n_labels * 4, "ms_per_step": ms_e2e / K},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "streaming_windows": streaming,
             "tensor_frac_of_burst_peak_whole_step": FLOPS_PER_UTT.get(args.model, 0) * value / world / 1e12 / pk["bf16_tflops"]}
     print(json.dumps(line))
     if world > 1:

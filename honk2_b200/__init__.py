@@ -14,6 +14,7 @@ from .zoo import MODEL_ZOO, model_config  # noqa: F401
 from ._native import NativeError  # noqa: F401
 from .profile import profile_layers  # noqa: F401
 from .workspace import load_checkpoint, strip_data_parallel_prefix  # noqa: F401
+from .streaming import n_stream_windows, stream_window_targets, evaluate_stream  # noqa: F401
 
 __version__ = "0.1.0"
 

@@ -87,6 +87,54 @@ class AudioProcessor(object):
                                                _stream_ptr(waves.device)), "kws_mfcc_forward")
         return out
 
+    # ---- streaming windows -------------------------------------------------------------
+    @staticmethod
+    def n_stream_windows(n_stream_samples, window_size, shift_size):
+        """Number of windows a stream yields: StreamingDataset.num_samples (dataset/dataset_utils.py:31)."""
+        return max(0, int((n_stream_samples - window_size) / shift_size))
+
+    def compute_mfccs_stream(self, stream, window_size=16000, shift_size=160, first=0, count=None, out=None):
+        """Features of the sliding windows of one audio stream, without materialising the windows.
+
+        stream: CUDA float32 [L]; window k = stream[k*shift_size : k*shift_size + window_size], exactly what
+        StreamingDataset.__getitem__ hands to collate_fn (dataset/dataset_utils.py:72, audio_data_loader.py:26-29;
+        gsc_dev_config.json:62-63: 16000 / 160 samples).  Returns CUDA float32 [count, T, n_mels] for windows
+        first .. first+count-1 (default: all StreamingDataset.num_samples of them), bit-identical to
+        compute_mfccs_batch on the stacked windows.  With shift_size a multiple of the 160-sample hop, 97 of a 1 s
+        window's 101 frames are shared with its neighbours and computed once."""
+        if not (isinstance(stream, torch.Tensor) and stream.is_cuda):
+            raise _native.NativeError("compute_mfccs_stream needs a CUDA tensor: there is no CPU path")
+        if stream.dim() != 1:
+            raise ValueError("compute_mfccs_stream expects a 1-D stream")
+        if window_size < 1 or shift_size < 1:
+            raise ValueError("window_size and shift_size must be positive")
+        if stream.dtype != torch.float32:
+            stream = stream.float()
+        stream = stream.contiguous()
+        total = self.n_stream_windows(stream.numel(), window_size, shift_size)
+        if count is None:
+            count = total - first
+        if first < 0 or count < 0 or first + count > total:
+            raise ValueError(f"windows {first}..{first + count} outside the stream's {total} windows")
+        T = self.n_frames(window_size)
+        if out is None:
+            out = torch.empty((count, T, self.n_mels), dtype=torch.float32, device=stream.device)
+        elif out.shape != (count, T, self.n_mels) or out.dtype != torch.float32 or not out.is_contiguous() \
+                or out.device != stream.device:
+            raise ValueError("out must be a contiguous float32 [count, T, n_mels] tensor on the input's device")
+        if count == 0:
+            return out
+        lib = _native.load()
+        fe = self._frontend(stream.device)
+        need = lib.kws_mfcc_stream_scratch_bytes(fe, count, window_size, shift_size)
+        scratch = torch.empty(max(need, 16), dtype=torch.uint8, device=stream.device)
+        base = stream.data_ptr() + 4 * first * shift_size
+        with torch.cuda.device(stream.device):
+            _native.check(lib.kws_mfcc_stream_forward(fe, C.c_void_p(base), count, window_size, shift_size,
+                                                      C.c_void_p(out.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                                      need, _stream_ptr(stream.device)), "kws_mfcc_stream_forward")
+        return out
+
     # ---- reference API -------------------------------------------------------------------
     def compute_mfccs(self, data, device=None):
         """1-D float np.ndarray -> float32 np.ndarray (T, n_mels, 1), like the reference.

@@ -24,6 +24,7 @@ constexpr int kNz = 240;            // complex FFT length
 constexpr int kFramesPerCta = 16;
 constexpr int kMfccThreads = 256;
 constexpr int kStageSamples = (kFramesPerCta - 1) * kHop + kNfft;  // 2880
+constexpr int kEdgeStageSamples = kFramesPerCta * kNfft;            // 7680: every frame slot stages its own 480 samples
 constexpr int kMaxMels = 64;
 
 struct FrontendTables {
@@ -42,7 +43,8 @@ struct Frontend {
   float f_min, f_max;
   void* dev_blob = nullptr;
   FrontendTables t{};
-  size_t smem_bytes = 0;
+  size_t smem_bytes = 0;         // batch kernel
+  size_t smem_bytes_edges = 0;   // window-edge kernel of the streaming front-end
 };
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -119,33 +121,53 @@ __device__ __forceinline__ void dft15(const float2 (&y)[15], float2 (&z)[15]) {
   }
 }
 
+// EDGES = false: a CTA computes 16 consecutive frames of one clip; clip b starts at wav + b * wav_stride (wav_stride = N
+// for a dense [B, N] batch, = the shift for overlapping windows of a stream).
+// EDGES = true (streaming front-end): a CTA computes the four frames of four windows that touch the reflect padding
+// (t = 0, 1, T-2, T-1); every other frame of a window is shared with the stream-level frame table.
+template <bool EDGES>
 __global__ void __launch_bounds__(kMfccThreads)
-mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t B, int N, int T,
+mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride, int64_t B, int N, int T,
             int tiles_per_utt, float* __restrict__ feat) {
+  constexpr int kStage = EDGES ? kEdgeStageSamples : kStageSamples;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* scratch = reinterpret_cast<float2*>(smem_raw);                 // [16][240]
   float2* s_tw240 = scratch + kFramesPerCta * kNz;                       // [240]
   float2* s_tw480 = s_tw240 + kNz;                                       // [240]
-  float* s_wave = reinterpret_cast<float*>(s_tw480 + kNz);               // [2880]
-  float* s_win = s_wave + kStageSamples;                                 // [480]
+  float* s_wave = reinterpret_cast<float*>(s_tw480 + kNz);               // [2880] ([16][480] for EDGES)
+  float* s_win = s_wave + kStage;                                        // [480]
   int* s_lo = reinterpret_cast<int*>(s_win + kNfft);                     // [64]
   int* s_cnt = s_lo + kMaxMels;
   int* s_off = s_cnt + kMaxMels;
   float* s_w = reinterpret_cast<float*>(s_off + kMaxMels);               // [nnz]
 
   const int tid = threadIdx.x;
-  const int64_t b = blockIdx.x / tiles_per_utt;
-  const int t0 = (blockIdx.x % tiles_per_utt) * kFramesPerCta;
-  const float* w = wav + b * (int64_t)N;
+  const int64_t b = EDGES ? (int64_t)blockIdx.x * 4 : blockIdx.x / tiles_per_utt;   // (EDGES: first of four windows)
+  const int t0 = EDGES ? 0 : (blockIdx.x % tiles_per_utt) * kFramesPerCta;
+  const float* w = wav + b * wav_stride;
 
-  // stage: samples [160*t0 - 240, +2880) with librosa 'reflect' padding at the clip edges
-  const int j0 = t0 * kHop - kNfft / 2;
-  for (int i = tid; i < kStageSamples; i += kMfccThreads) {
-    int j = j0 + i;
-    if (j < 0) j = -j;
-    if (j >= N) j = 2 * (N - 1) - j;
-    j = max(0, min(j, N - 1));  // only reachable for samples of masked frames
-    s_wave[i] = __ldg(w + j);
+  if constexpr (EDGES) {
+    // frame slot s = 4 * (window - b) + e, e -> frame t = 0, 1, T-2, T-1: samples [160 t - 240, +480) of its window
+    for (int i = tid; i < kEdgeStageSamples; i += kMfccThreads) {
+      const int slot = i / kNfft, n = i - slot * kNfft;
+      const int wi = slot >> 2, e = slot & 3;
+      const int te = e < 2 ? e : T - 4 + e;
+      int j = te * kHop - kNfft / 2 + n;
+      if (j < 0) j = -j;
+      if (j >= N) j = 2 * (N - 1) - j;
+      j = max(0, min(j, N - 1));
+      s_wave[i] = b + wi < B ? __ldg(w + (int64_t)wi * wav_stride + j) : 0.f;
+    }
+  } else {
+    // stage: samples [160*t0 - 240, +2880) with librosa 'reflect' padding at the clip edges
+    const int j0 = t0 * kHop - kNfft / 2;
+    for (int i = tid; i < kStageSamples; i += kMfccThreads) {
+      int j = j0 + i;
+      if (j < 0) j = -j;
+      if (j >= N) j = 2 * (N - 1) - j;
+      j = max(0, min(j, N - 1));  // only reachable for samples of masked frames
+      s_wave[i] = __ldg(w + j);
+    }
   }
   for (int i = tid; i < kNfft; i += kMfccThreads) s_win[i] = tb.window[i];
   for (int i = tid; i < kNz; i += kMfccThreads) { s_tw240[i] = tb.tw240[i]; s_tw480[i] = tb.tw480[i]; }
@@ -158,9 +180,10 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t B, int N, 
   const int warp = tid >> 5, lane = tid & 31;
   const int half = lane >> 4, l = lane & 15;
   const int t_local = 2 * warp + half;
-  const int t = t0 + t_local;
+  const int t = EDGES ? ((t_local & 3) < 2 ? (t_local & 3) : T - 4 + (t_local & 3)) : t0 + t_local;
+  const int64_t b_out = EDGES ? b + (t_local >> 2) : b;
   float2* sc = scratch + t_local * kNz;
-  const float* fr = s_wave + kHop * t_local;
+  const float* fr = s_wave + (EDGES ? kNfft : kHop) * t_local;
 
   // ---- stage A: 15 radix-16 FFTs over n1 (lane = n2), twiddle by W240^(n2 k1)
   if (l < 15) {
@@ -218,14 +241,28 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t B, int N, 
   __syncwarp();
 
   // ---- sparse mel filterbank, ln, x2 (reference "DCT" of a length-1 axis)
-  if (t < T) {
-    float* out = feat + (b * (int64_t)T + t) * tb.n_mels;
+  if (t < T && b_out < B) {
+    float* out = feat + (b_out * (int64_t)T + t) * tb.n_mels;
     for (int m = l; m < tb.n_mels; m += 16) {
       const int lo = s_lo[m], cnt = s_cnt[m], off = s_off[m];
       float acc = 0.f;
       for (int i = 0; i < cnt; ++i) acc = fmaf(s_w[off + i], P[lo + i], acc);
       out[m] = acc > 0.f ? 2.f * logf(acc) : 2.f * acc;
     }
+  }
+}
+
+// Streaming front-end: interior frames of window k (t = 2 .. T-3) are rows (k * m + t) of the stream-level frame
+// table S (m = shift / hop).  Pure copy, 16 bytes per thread when the row length allows.
+template <typename V>
+__global__ void __launch_bounds__(256)
+mfcc_stream_gather_kernel(const V* __restrict__ S, int64_t K, int T, int m, int row_v, V* __restrict__ feat) {
+  const int64_t per_win = (int64_t)(T - 4) * row_v;
+  const int64_t total = K * per_win;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i / per_win;
+    const int64_t r = i - k * per_win;   // (t - 2) * row_v + c
+    feat[k * (int64_t)T * row_v + 2 * row_v + r] = __ldg(S + (k * m + 2) * (int64_t)row_v + r);
   }
 }
 
@@ -337,7 +374,10 @@ extern "C" int kws_frontend_create(int sr, int n_mels, float f_min, float f_max,
   fe->smem_bytes = sizeof(float2) * (kFramesPerCta * kNz + 2 * kNz) +
                    sizeof(float) * (kStageSamples + kNfft) + sizeof(int) * 3 * kMaxMels +
                    sizeof(float) * (nnz + 1);
-  e = cudaFuncSetAttribute(mfcc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes);
+  fe->smem_bytes_edges = fe->smem_bytes + sizeof(float) * (kEdgeStageSamples - kStageSamples);
+  e = cudaFuncSetAttribute(mfcc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(mfcc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes_edges);
   if (e != cudaSuccess) {
     set_error("kws_frontend_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     cudaFree(fe->dev_blob);
@@ -374,8 +414,68 @@ extern "C" int kws_mfcc_forward(const kws_frontend_t* fe, const float* wav, int6
   const int tiles = ceil_div(T, kFramesPerCta);
   const int64_t blocks = B * tiles;
   KWS_REQUIRE(blocks < (int64_t)2147483647, "kws_mfcc_forward: batch too large for one launch");
-  mfcc_kernel<<<(unsigned)blocks, kMfccThreads, fe->smem_bytes, as_stream(stream)>>>(
-      fe->t, wav, B, n_samples, T, tiles, feat);
+  mfcc_kernel<false><<<(unsigned)blocks, kMfccThreads, fe->smem_bytes, as_stream(stream)>>>(
+      fe->t, wav, (int64_t)n_samples, B, n_samples, T, tiles, feat);
+  KWS_CHECK_LAUNCH();
+  return KWS_OK;
+}
+
+extern "C" size_t kws_mfcc_stream_scratch_bytes(const kws_frontend_t* fe, int64_t n_windows, int window, int shift) {
+  if (!fe || n_windows < 1 || window < 1 || shift < 1) return 0;
+  const int T = 1 + window / kHop;
+  if (shift % kHop != 0 || T < 5) return 0;   // no frame is shared: computed straight into the output
+  const int64_t span = (n_windows - 1) * (int64_t)shift + window;
+  return (size_t)(1 + span / kHop) * fe->n_mels * sizeof(float);
+}
+
+extern "C" int kws_mfcc_stream_forward(const kws_frontend_t* fe, const float* wav, int64_t n_windows, int window,
+                                       int shift, float* feat, void* scratch, size_t scratch_bytes, void* stream) {
+  KWS_REQUIRE(fe != nullptr, "kws_mfcc_stream_forward: frontend is null");
+  KWS_REQUIRE(n_windows >= 0, "kws_mfcc_stream_forward: negative window count");
+  KWS_REQUIRE(window > kNfft / 2, "kws_mfcc_stream_forward: need more than %d samples per window (got %d)",
+              kNfft / 2, window);
+  KWS_REQUIRE(shift >= 1, "kws_mfcc_stream_forward: shift must be positive (got %d)", shift);
+  if (n_windows == 0) return KWS_OK;
+  KWS_REQUIRE(wav != nullptr && feat != nullptr, "kws_mfcc_stream_forward: null buffer");
+  cudaStream_t st = as_stream(stream);
+  const int T = 1 + window / kHop;
+  const int tiles = ceil_div(T, kFramesPerCta);
+  const int64_t span = (n_windows - 1) * (int64_t)shift + window;   // samples the windows cover
+  if (shift % kHop != 0 || T < 5) {
+    // windows do not share frames (or have no interior frame): every window in full, read in place from the stream
+    const int64_t blocks = n_windows * tiles;
+    KWS_REQUIRE(blocks < (int64_t)2147483647, "kws_mfcc_stream_forward: too many windows for one launch");
+    mfcc_kernel<false><<<(unsigned)blocks, kMfccThreads, fe->smem_bytes, st>>>(
+        fe->t, wav, (int64_t)shift, n_windows, window, T, tiles, feat);
+    KWS_CHECK_LAUNCH();
+    return KWS_OK;
+  }
+  KWS_REQUIRE(span < (int64_t)2147483647, "kws_mfcc_stream_forward: the windows cover %lld samples; split the call",
+              (long long)span);
+  const size_t need = kws_mfcc_stream_scratch_bytes(fe, n_windows, window, shift);
+  KWS_REQUIRE(scratch != nullptr && scratch_bytes >= need,
+              "kws_mfcc_stream_forward: needs %zu bytes of scratch, got %zu", need, scratch_bytes);
+  // 1) the frame table of the whole span as ONE clip: rows 2 .. J-3 do not touch its reflect padding
+  float* S = static_cast<float*>(scratch);
+  const int J = 1 + (int)(span / kHop);
+  mfcc_kernel<false><<<(unsigned)ceil_div(J, kFramesPerCta), kMfccThreads, fe->smem_bytes, st>>>(
+      fe->t, wav, span, (int64_t)1, (int)span, J, ceil_div(J, kFramesPerCta), S);
+  KWS_CHECK_LAUNCH();
+  // 2) the four frames per window that do (reflect padding at the WINDOW's edges, audio_processor.py:19-26 per window)
+  mfcc_kernel<true><<<(unsigned)ceil_div<int64_t>(n_windows, 4), kMfccThreads, fe->smem_bytes_edges, st>>>(
+      fe->t, wav, (int64_t)shift, n_windows, window, T, 1, feat);
+  KWS_CHECK_LAUNCH();
+  // 3) interior frames: copies of table rows
+  const int m = shift / kHop;
+  const bool vec = fe->n_mels % 4 == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
+  const int row_v = vec ? fe->n_mels / 4 : fe->n_mels;
+  const int64_t total = n_windows * (int64_t)(T - 4) * row_v;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(total, 256), 148 * 16);
+  if (vec)
+    mfcc_stream_gather_kernel<float4><<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(S), n_windows, T, m, row_v,
+                                                            reinterpret_cast<float4*>(feat));
+  else
+    mfcc_stream_gather_kernel<float><<<grid, 256, 0, st>>>(S, n_windows, T, m, row_v, feat);
   KWS_CHECK_LAUNCH();
   return KWS_OK;
 }

@@ -59,6 +59,16 @@ int kws_frontend_n_frames(const kws_frontend_t* fe, int n_samples);
 int kws_frontend_n_mels(const kws_frontend_t* fe);
 int kws_mfcc_forward(const kws_frontend_t* fe, const float* wav, int64_t B, int n_samples,
                      float* feat, void* stream);
+/* Streaming-window front-end: replaces StreamingDataset.__getitem__'s window slicing
+ * (dataset/dataset_utils.py:28-31,72 -- window k = stream[k*shift : k*shift + window]) followed by the per-window
+ * compute_mfccs of collate_fn (audio_data_loader.py:26-29).  wav points at the first sample of the first window and
+ * must hold (n_windows-1)*shift + window samples; feat [n_windows, T, n_mels] is bit-identical to kws_mfcc_forward on
+ * the materialised windows.  When shift is a multiple of the hop (gsc_dev_config.json:62-63: 1000 ms / 10 ms), every
+ * frame that does not touch a window's reflect padding (t = 2 .. T-3) is computed ONCE per stream position and copied;
+ * only 4 frames per window are computed per window.  scratch: kws_mfcc_stream_scratch_bytes (0 = none needed). */
+size_t kws_mfcc_stream_scratch_bytes(const kws_frontend_t* fe, int64_t n_windows, int window, int shift);
+int kws_mfcc_stream_forward(const kws_frontend_t* fe, const float* wav, int64_t n_windows, int window, int shift,
+                            float* feat, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- models: replace model.ResNet / model.CNN ---------------------------------------------
  * kws_resnet_create <- ResNet.__init__ (model/resnet.py:11-36); pool_h = pool_w = 0 when the

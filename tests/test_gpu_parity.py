@@ -93,6 +93,74 @@ def test_mfcc_batch_is_per_utterance(dev):
         assert torch.equal(full[b], ap.compute_mfccs_batch(w[b:b + 1])[0])
 
 
+@pytest.mark.parametrize("window,shift", [(16000, 160), (16000, 320), (16000, 100), (8000, 160), (700, 160),
+                                          (16001, 480), (144000, 1600)])
+def test_mfcc_stream_windows_equal_materialised_windows(dev, window, shift):
+    """Streaming front-end (dataset_utils.py:28-31,72 + audio_data_loader.py:26-29): the features of
+    window k must be BIT-identical to compute_mfccs_batch on stream[k*shift : k*shift+window], whether frames are
+    shared (shift a multiple of the 160-sample hop) or not (shift 100; T < 5), and agree with the CPU oracle."""
+    ap = AudioProcessor()
+    n_win = 37 if window < 100000 else 5
+    L = (n_win + 1) * shift + window - 1          # int((L - window) / shift) == n_win
+    stream = torch.from_numpy(synth.speechlike(1, N=L, seed=window + shift)[0]).to(dev)
+    assert ap.n_stream_windows(L, window, shift) == n_win
+    got = ap.compute_mfccs_stream(stream, window, shift)
+    windows = torch.stack([stream[k * shift:k * shift + window] for k in range(n_win)])
+    want = ap.compute_mfccs_batch(windows)
+    assert got.shape == want.shape == (n_win, 1 + window // 160, 40)
+    assert torch.equal(got, want)
+    # a sub-range of the windows, into a caller-provided buffer
+    out = torch.full((5, 1 + window // 160, 40), float("nan"), device=dev) if n_win >= 9 else None
+    if out is not None:
+        ap.compute_mfccs_stream(stream, window, shift, first=3, count=5, out=out)
+        assert torch.equal(out, want[3:8])
+    ks = [0, n_win - 1]
+    ref = mfcc_ref.compute_mfccs_batch(windows[ks].cpu().numpy())
+    assert scaled_err(got[ks].cpu().numpy(), ref) <= MFCC_TOL
+
+
+def test_mfcc_stream_at_batch_size_and_argument_errors(dev):
+    """8192 windows of 1 s at a 10 ms shift (gsc_dev_config.json:62-63) from a 83 s stream: 4 frames per window are
+    computed per window, the other 97 come from the 8293-row stream frame table."""
+    ap = AudioProcessor()
+    L = 8192 * 160 + 16000 + 159
+    stream = torch.from_numpy(synth.broadband(1, N=L, seed=9)[0]).to(dev)
+    got = ap.compute_mfccs_stream(stream, 16000, 160)
+    assert got.shape == (8192, 101, 40)
+    idx = [0, 1, 4095, 8191]
+    windows = torch.stack([stream[k * 160:k * 160 + 16000] for k in idx])
+    assert torch.equal(got[idx], ap.compute_mfccs_batch(windows))
+    # consecutive windows share their interior frames
+    assert torch.equal(got[1:, 2:98], got[:-1, 3:99])
+    with pytest.raises(ValueError):
+        ap.compute_mfccs_stream(stream, 16000, 160, first=8000, count=500)
+    with pytest.raises(ValueError):
+        ap.compute_mfccs_stream(stream.unsqueeze(0))
+    with pytest.raises(honk2_b200.NativeError):
+        ap.compute_mfccs_stream(stream, 200, 160)       # reflect padding needs more than 240 samples
+
+
+def test_evaluate_stream_matches_window_by_window_evaluation(dev):
+    """evaluate_stream == slicing the windows like StreamingDataset, collating them and running evaluate's loop."""
+    from honk2_b200.streaming import evaluate_stream, stream_window_targets
+    ap = AudioProcessor()
+    m, _ = gpu_model("res8", "hardened", dev)
+    rng = np.random.default_rng(4)
+    lens = rng.integers(3000, 20000, 12)
+    labs = rng.integers(0, 12, 12)
+    stream = torch.from_numpy(synth.speechlike(1, N=int(lens.sum()), seed=8)[0]).to(dev)
+    targets = stream_window_targets(lens, labs, 12, 16000, 1600)
+    logits, stats = evaluate_stream(m, ap, stream, 16000, 1600, targets=targets, batch_size=32)
+    n = len(targets)
+    windows = torch.stack([stream[k * 1600:k * 1600 + 16000] for k in range(n)])
+    with torch.no_grad():
+        want = m(ap.compute_mfccs_batch(windows))
+    assert logits.shape == (n, 12)
+    assert float((logits - want).abs().max()) <= 1e-4 * float(want.abs().max())
+    assert stats["total"] == n
+    assert stats["correct"] == int((want.argmax(1).cpu().numpy() == targets).sum())
+
+
 def test_mfcc_large_batch_statistics(dev):
     """BASELINE size (8192 x 1 s): spot-check 16 random rows against the oracle."""
     ap = AudioProcessor()

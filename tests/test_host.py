@@ -180,6 +180,48 @@ def test_audio_processor_signature():
         ap.compute_pcen(np.zeros(10, dtype=np.float32))
 
 
+def test_stream_window_targets_match_reference_bookkeeping():
+    """StreamingDataset.__getitem__ (dataset_utils.py:47-95), restated in oracle/stream_ref.py: window slices and
+    majority-vote targets (lowest label wins ties) for random labelled segment streams."""
+    from honk2_b200.streaming import n_stream_windows, stream_window_targets
+    from oracle import stream_ref
+    rng = np.random.default_rng(0)
+    checked = 0
+    for _ in range(80):
+        n_labels = int(rng.integers(2, 6))
+        n_seg = int(rng.integers(3, 10))
+        lens = rng.integers(1, 50, n_seg)
+        labs = rng.integers(0, n_labels, n_seg)
+        window = int(rng.integers(4, 40))
+        shift = int(rng.integers(1, min(10, window) + 1))
+        n = n_stream_windows(int(lens.sum()), window, shift)
+        assert n == max(0, int((int(lens.sum()) - window) / shift))       # dataset_utils.py:31
+        if n <= 0:
+            continue
+        segs = [rng.standard_normal(l) for l in lens]
+        stream = np.concatenate(segs)
+        ref = list(stream_ref.iterate_windows(segs, list(labs), n_labels, window, shift, n))
+        got = stream_window_targets(lens, labs, n_labels, window, shift)
+        assert [t for _, t in ref] == list(got)
+        for k, (w, _) in enumerate(ref):
+            assert np.array_equal(w, stream[k * shift:k * shift + window])
+        checked += 1
+    assert checked >= 40
+    # ties: equal halves -> the lower label index (strict ">" while enumerating, dataset_utils.py:76-79)
+    assert list(stream_window_targets([4, 4, 8], [3, 1, 2], 4, 8, 4)) == [1, 1]
+    with pytest.raises(ValueError):
+        stream_window_targets([4, 4], [0, 5], 4, 4, 2)
+    with pytest.raises(ValueError):
+        stream_window_targets([4, 4], [0, 1], 2, 4, 1, n_windows=100)
+
+
+def test_stream_frontend_has_no_cpu_path():
+    ap = honk2_b200.AudioProcessor()
+    assert ap.n_stream_windows(16000 * 10, 16000, 160) == 900
+    with pytest.raises(honk2_b200.NativeError):
+        ap.compute_mfccs_stream(torch.zeros(40000))
+
+
 # ---- the C-ABI library ---------------------------------------------------------------------------
 
 def header_symbols():
@@ -211,6 +253,9 @@ def test_argument_errors_without_gpu(native_lib):
     assert b"model is null" in native_lib.kws_last_error()
     assert native_lib.kws_frontend_n_frames(None, 16000) == 0
     assert native_lib.kws_model_workspace_bytes(None, 1, 101, 40, 0) == 0
+    assert native_lib.kws_mfcc_stream_scratch_bytes(None, 10, 16000, 160) == 0
+    assert native_lib.kws_mfcc_stream_forward(None, None, 1, 16000, 160, None, None, 0, None) == 1
+    assert b"frontend is null" in native_lib.kws_last_error()
     out = ctypes.c_void_p()
     assert native_lib.kws_frontend_create(16000, 40, 20.0, 4000.0, 512, 160, ctypes.byref(out)) == 1
     assert b"n_fft=480" in native_lib.kws_last_error()
