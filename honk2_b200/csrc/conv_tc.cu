@@ -190,6 +190,11 @@ __device__ __forceinline__ void st_hint(uint4* ptr, const uint4& v, uint64_t pol
   asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
                ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
+// one 32-byte store per thread (STG.256, sm_100): a whole sector, no half-sector write pairs
+__device__ __forceinline__ void st_hint256(uint4* ptr, const uint4& a, const uint4& b, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
+               ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void tma_load_5d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
                                                  int c2, int c3, int c4, uint64_t pol) {
   asm volatile(
@@ -244,6 +249,19 @@ __device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, ui
       "mov.b64 db, {%2, %3};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "n"(kAccumulate ? 1 : 0)
+      : "memory");
+}
+// Same, A and B descriptors with their own high words (different swizzle modes).
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_f16_lohi2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(kAccumulate ? 1 : 0)
       : "memory");
 }
 __device__ __forceinline__ void umma_f16_lohi_rt(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
@@ -916,6 +934,7 @@ struct TcResNet {
   int fused_smem = 0;
   // column-sweep whole-network kernel (resnet_sweep.cuh), preferred when the map is tall enough
   bool sweep_enabled = true;
+  bool sweep_k32 = true;       // HONK2_TC_SWEEP_K32=0 disables: 16-channel rows, swizzle-32B staging (single-strip maps)
   bool sweep_packed = false;   // HONK2_TC_SWEEP_PACKED=1: whole columns contiguous in HBM (one bulk copy per step; measured slower, see tc_sweep_plan)
   void* sweep_dev = nullptr;   // [SwLayerDesc x n_layers][pad][CUtensorMap x n_layers]
   std::tuple<int, int, const void*> sweep_key{-1, -1, nullptr};
@@ -1073,6 +1092,7 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
     const char* senv = std::getenv("HONK2_TC_SWEEP");
     p->sweep_enabled = senv == nullptr || std::atoi(senv) != 0;
     { const char* e = std::getenv("HONK2_TC_SWEEP_PACKED"); p->sweep_packed = e != nullptr && std::atoi(e) != 0; }
+    { const char* e = std::getenv("HONK2_TC_SWEEP_K32"); p->sweep_k32 = e == nullptr || std::atoi(e) != 0; }
     const char* env = std::getenv("HONK2_TC_LANES");
     p->lanes = env ? std::max(1, std::min(kTcMaxLanes, std::atoi(env))) : 2;
     bool ok = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) == cudaSuccess;
@@ -1349,7 +1369,7 @@ struct TcSweepPlan {
   int n_slots = 0, n_strips = 0, smem_total = 0, n_stages = 0;
   int c0w_off = 0, w_off[2] = {0, 0}, skip_off = 0, ring_off = 0, slot_bytes = 0;
   int dmax = 1, col_rows = 0;
-  bool bulk = false, packed = false;   // staging by bulk copies; whole columns contiguous in HBM (resnet_sweep.cuh)
+  bool bulk = false, packed = false, k32 = false;   // staging by bulk copies; whole columns contiguous in HBM (resnet_sweep.cuh)
   std::vector<int> dil;
 };
 
@@ -1392,6 +1412,10 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W) {
   // the TMA-box fallback keeps the dense pitch its tensor maps describe
   static const bool col_align = [] { const char* e = std::getenv("HONK2_TC_SWEEP_COLALIGN"); return e != nullptr && std::atoi(e) != 0; }();
   f.col_rows = (bulk_on && col_align) ? round_up(H, 8) : H;
+  // 16 channels per row (HONK2_TC_SWEEP_K32): [K chunk][w][h][32 B] in HBM, swizzle-32B operand in shared memory,
+  // NKC bulk copies per step instead of 2*NKC (resnet_sweep.cuh)
+  f.k32 = bulk_on && p->sweep_k32 && !f.packed && f.n_strips == 1;
+  if (f.k32) f.col_rows = H;
   int slack = 0;
   if (f.packed) {
     f.slot_bytes = round_up((p->NP * (H + dmax) + dmax) * 16, 128);
@@ -1414,17 +1438,19 @@ static size_t tc_sweep_ws_bytes(const TcResNet* p, const TcSweepPlan& f, int H, 
   return 2 * buf;
 }
 
-template <int NKC>
-static int tc_launch_sweep(const SwParams& prm, int grid, int smem, cudaStream_t st) {
-  if (prm.debug != nullptr) {
-    KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    resnet_tc_sweep_kernel<NKC, true><<<grid, sw_threads(NKC), smem, st>>>(prm);
-  } else {
-    KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    resnet_tc_sweep_kernel<NKC, false><<<grid, sw_threads(NKC), smem, st>>>(prm);
-  }
+template <int NKC, bool DBG, bool K32>
+static int tc_launch_sweep_v(const SwParams& prm, int grid, int smem, cudaStream_t st) {
+  KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC, DBG, K32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  resnet_tc_sweep_kernel<NKC, DBG, K32><<<grid, sw_threads(NKC), smem, st>>>(prm);
   KWS_CHECK_LAUNCH();
   return KWS_OK;
+}
+
+template <int NKC>
+static int tc_launch_sweep(const SwParams& prm, int grid, int smem, cudaStream_t st) {
+  if (prm.debug != nullptr)
+    return prm.k32 ? tc_launch_sweep_v<NKC, true, true>(prm, grid, smem, st) : tc_launch_sweep_v<NKC, true, false>(prm, grid, smem, st);
+  return prm.k32 ? tc_launch_sweep_v<NKC, false, true>(prm, grid, smem, st) : tc_launch_sweep_v<NKC, false, false>(prm, grid, smem, st);
 }
 
 static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat, int64_t B, int T, int F, int H, int W,
@@ -1483,6 +1509,7 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
     q.bulk_rows = f.bulk ? H : 0;
     q.packed = f.packed ? 1 : 0;
     q.col_rows = f.col_rows;
+    q.k32 = f.k32 ? 1 : 0;
     {
       const char* e = std::getenv("HONK2_TC_SWEEP_DISCARD");
       q.discard_q = (e ? std::atoi(e) != 0 : true) && f.n_strips == 1;

@@ -104,13 +104,16 @@ struct SwParams {
   int dmax;                     // largest dilation of the network (bulk path: data row h sits at slot row dmax + h)
   int packed;                   // 1 = P / Q hold whole COLUMNS contiguously, [w][pad dmax | plane 0 | pad | plane 1 | ... | pad] (single strip)
   int col_rows;                 // planar layout: rows between consecutive columns of a plane (H, or H rounded up to 8 = whole 128-byte lines)
+  int k32;                      // 1 = activations as [K chunk][w][h][16 channels = 32 B] (single strip): NKC copies per step,
+                                //     swizzle-32B A operand; the two 16-byte halves of a row are stored swapped where
+                                //     ((dmax + h) >> 2) & 1, i.e. exactly as the linear copy must land them in the slot
   int discard_q;                // 1 = Q columns are discarded from L2 (no write-back) once the layer that reads them has consumed them
   int diag;                     // diagnostics (wrong results!): 1 = epilogue skips math and stores, 2 = skips the skip-tensor loads
   long long* debug;             // optional cycle counters of CTA 0 (HONK2_TC_DEBUG=1)
   long long* trace;             // optional [8][kSwTraceLen] event timestamps of CTA 0 (HONK2_TC_TRACE=1, needs DEBUG)
 };
 
-template <int NKC, bool DBG>
+template <int NKC, bool DBG, bool K32>
 __global__ void __launch_bounds__(sw_threads(NKC), 1)
 resnet_tc_sweep_kernel(const SwParams p) {
   constexpr int kEpiWarps = sw_epi_warps(NKC);
@@ -152,6 +155,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
   // The packed form makes a staged column ONE contiguous run: one bulk copy per step instead of NP, and the zero rows
   // between planes (shared by the plane above and the plane below) are the convolution's height padding.
   const bool packed = p.packed != 0;
+  constexpr bool k32 = K32;   // (compile time: the two layouts' address arithmetic would not fit the epilogue's registers together)
+  const int64_t kc_stride = (int64_t)W * H * 2;   // k32: 16-byte units between K chunks
   const int PP = H + p.dmax;                    // packed: plane pitch (rows)
   const int COLP = NP * PP + p.dmax;            // packed: column pitch (rows)
   const int col_pitch = packed ? COLP : p.col_rows, col_base = packed ? p.dmax : 0;
@@ -336,6 +341,11 @@ resnet_tc_sweep_kernel(const SwParams p) {
                           const __nv_bfloat16 lo = __float2bfloat16_rn(fv[c] - __bfloat162float(hi));
                           const uint32_t packed = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
                           unsigned char* slot = smem + p.smem_ring_off + (size_t)st[c] * p.ring_slot_bytes;
+                          if (k32) {   // 32-byte rows: channels 0-7 in the (swizzled) first half, zeros in the other
+                            const int row = r0 + rr, sw = (row >> 2) & 1;
+                            *reinterpret_cast<uint4*>(slot + (size_t)row * 32 + (sw << 4)) = make_uint4(packed, 0u, 0u, 0u);
+                            *reinterpret_cast<uint4*>(slot + (size_t)row * 32 + ((sw ^ 1) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                          } else
                           *reinterpret_cast<uint4*>(slot + (size_t)(r0 + rr) * 16) = make_uint4(packed, 0u, 0u, 0u);
                         }
                       }
@@ -370,7 +380,18 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 mbar_wait_lean(empty_bar(stage), sphase ^ 1);
                 pstamp(pd_empty);
                 const uint32_t dst = sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes;
-                if (packed) {
+                if (k32) {
+                  // one contiguous H x 32 B run per 16-channel chunk
+                  if (leader) {
+                    const uint32_t bytes = (uint32_t)H * 32u;
+                    mbar_expect_tx(full_bar(stage), bytes * NKC);
+                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)w * H * 2;
+                    const uint32_t d0 = dst + (uint32_t)p.dmax * 32u;
+#pragma unroll
+                    for (int kc = 0; kc < NKC; ++kc)
+                      bulk_load_hint(d0 + (uint32_t)(kc * box_rows) * 32u, src + kc * kc_stride, bytes, full_bar(stage), pol);
+                  }
+                } else if (packed) {
                   // the whole column, zero rows included, in one copy
                   if (leader) {
                     mbar_expect_tx(full_bar(stage), (uint32_t)COLP * 16u);
@@ -485,7 +506,12 @@ resnet_tc_sweep_kernel(const SwParams p) {
           const int cur = (int)(sq & 1);
           const uint32_t plane16 = (uint32_t)box_rows;                       // plane pitch in 16-byte units
           // (conv_0: both K halves read plane 0, the weights of the second half are zero)
-          const uint32_t a_lbo = is_c0 ? 0u : (plane16 & 0x3FFFu) << 16;
+          const uint32_t a_lbo = k32 ? (1u << 16) : is_c0 ? 0u : (plane16 & 0x3FFFu) << 16;
+          // A descriptor high word: SWIZZLE_NONE, SBO = 128 B -- or SWIZZLE_32B (layout type 6), SBO = 256 B per 8 rows
+          // (the swizzle is applied to absolute shared-memory addresses, so any row offset works: tools/umma_bench5)
+          const uint32_t a_hi = k32 ? ((256u >> 4) | (1u << 14) | (6u << 29)) : desc_hi;
+          const uint32_t row_mul = k32 ? 2u : 1u;                                    // 16-byte units per row
+          const uint32_t kc_step = k32 ? (uint32_t)box_rows * 2u : 2u * plane16;     // 16-byte units per K chunk
           const uint32_t w16 = ((sbase + (is_c0 ? p.smem_c0w_off : p.smem_w_off[wq & 1])) >> 4);
           const uint32_t row0 = (uint32_t)row0_of(d);
           stamp(dbg_other);
@@ -518,7 +544,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   if constexpr (DBG) { if (is_c0 && s == 0 && r == 0 && i < kSwIssuers) stamp(dbg_utt); else stamp(dbg_full); }
                   // All operands of the step are computed BEFORE the burst, and the burst is straight-line code
                   // without predicated-off MMAs (separate path for the wrapped window).
-                  const uint32_t a16 = ((sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes) >> 4) + row0;
+                  const uint32_t a16 = ((sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes) >> 4) + row0 * row_mul;
                   const uint32_t d1 = tmem_u + (uint32_t)(p0 * CP);
                   const uint32_t id1 = idesc0 + (uint32_t)wrap_at * idesc_blk;
                   uint32_t al[3 * NKC], bl[3 * NKC];
@@ -526,7 +552,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   for (int kc = 0; kc < NKC; ++kc)
 #pragma unroll
                     for (int dh = 0; dh < 3; ++dh) {
-                      al[kc * 3 + dh] = ((a16 + (uint32_t)(2 * kc) * plane16 + (uint32_t)(dh * d)) & 0x3FFFu) | a_lbo;
+                      al[kc * 3 + dh] = ((a16 + (uint32_t)kc * kc_step + (uint32_t)(dh * d) * row_mul) & 0x3FFFu) | a_lbo;
                       bl[kc * 3 + dh] = ((w16 + (uint32_t)(((kc * 3 + dh) * W_SLAB) >> 4) + (uint32_t)blk0 * blk16) & 0x3FFFu) | b_lbo;
                     }
                   // The burst token: bursts are issued one issuer at a time, in step order.  Without it the three
@@ -542,27 +568,27 @@ resnet_tc_sweep_kernel(const SwParams p) {
                     // conv_0: one 16-channel chunk (k = 0 .. 2 are its three height taps)
                     if (wrap_at == n) {
 #pragma unroll
-                      for (int k = 0; k < 3; ++k) umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
+                      for (int k = 0; k < 3; ++k) umma_f16_lohi2<true>(d1, al[k], a_hi, bl[k], desc_hi, id1);
                     } else {
                       const uint32_t id2 = idesc0 + (uint32_t)(n - wrap_at) * idesc_blk;
                       const uint32_t bo2 = (uint32_t)wrap_at * blk16;
 #pragma unroll
                       for (int k = 0; k < 3; ++k) {
-                        umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
-                        umma_f16_lohi<true>(tmem_u, al[k], bl[k] + bo2, desc_hi, id2);
+                        umma_f16_lohi2<true>(d1, al[k], a_hi, bl[k], desc_hi, id1);
+                        umma_f16_lohi2<true>(tmem_u, al[k], a_hi, bl[k] + bo2, desc_hi, id2);
                       }
                     }
                   } else if (wrap_at == n) {
 #pragma unroll
-                    for (int k = 0; k < 3 * NKC; ++k) umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
+                    for (int k = 0; k < 3 * NKC; ++k) umma_f16_lohi2<true>(d1, al[k], a_hi, bl[k], desc_hi, id1);
                   } else {
                     // the window wraps around the ring: first wrap_at blocks at p0, the rest from slot 0
                     const uint32_t id2 = idesc0 + (uint32_t)(n - wrap_at) * idesc_blk;
                     const uint32_t bo2 = (uint32_t)wrap_at * blk16;
 #pragma unroll
                     for (int k = 0; k < 3 * NKC; ++k) {
-                      umma_f16_lohi<true>(d1, al[k], bl[k], desc_hi, id1);
-                      umma_f16_lohi<true>(tmem_u, al[k], bl[k] + bo2, desc_hi, id2);   // (weights end far below 256 KB: no carry out of the address field)
+                      umma_f16_lohi2<true>(d1, al[k], a_hi, bl[k], desc_hi, id1);
+                      umma_f16_lohi2<true>(tmem_u, al[k], a_hi, bl[k] + bo2, desc_hi, id2);   // (weights end far below 256 KB: no carry out of the address field)
                     }
                   }
                   if (leader) {
@@ -671,7 +697,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
               if (mine) {
                 const int row = it.s * 128 + q * 32 + lane;
                 ob.exists = true; ob.w = it.w; ob.s = it.s; ob.slot = esl; ob.par = epr;
-                ob.off = row < H ? it.w * col_pitch + col_base + row : -1;
+                ob.off = row >= H ? -1 : k32 ? (it.w * H + row) * 2 : it.w * col_pitch + col_base + row;
               }
               // step the iterator, the ring slot and the owner
               ++it.o; it.w += d;
@@ -699,12 +725,25 @@ resnet_tc_sweep_kernel(const SwParams p) {
             // this lane's row of the staged skip column: [plane][128 rows][16 B]
             const uint32_t sk_addr = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT + (uint32_t)(q * 32 + lane) * 16u;
             const uint32_t sk_plane = packed ? (uint32_t)PP * 16u : 2048u;
+            // k32: this lane's row, and whether its two 16-byte halves are stored swapped
+            const uint32_t swl = (uint32_t)((p.dmax + q * 32 + lane) >> 2) & 1u;
+            const uint32_t sk_addr32 = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT + (uint32_t)(q * 32 + lane) * 32u;
             if constexpr (HAS_SKIP) {
               // This layer READS Q (the previous layer's output), one column per step, and the MMAs of this block were
               // the last consumers of Q column w.  Nothing reads that column again before the next even layer rewrites
               // it, so its dirty lines need not ever reach HBM: discard the 128-byte lines that lie wholly inside the
               // column (lines shared with the neighbouring columns stay).  One line per lane, planes 16 lanes apart.
-              if (p.discard_q) {
+              if (p.discard_q && k32) {
+                const int t = q * 32 + lane, kc = t >> 5, j = t & 31;   // H * 32 B <= 32 lines per chunk column
+                if (kc < NKC) {
+                  const char* qb = reinterpret_cast<const char*>(bufQ);
+                  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(qb) & 127u);
+                  const uint32_t o0 = (uint32_t)((kc * W + ob.w) * H) * 32u + mis;
+                  const uint32_t a = ((o0 + 127u) & ~127u) + (uint32_t)j * 128u;
+                  if (a + 128u <= o0 + (uint32_t)H * 32u)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(qb + (a - mis)) : "memory");
+                }
+              } else if (p.discard_q) {
                 const int t = q * 32 + lane, pl = t >> 4, j = t & 15;
                 if (pl < NP) {
                   // (single strip: H <= 128 rows = at most 16 lines per plane, one per lane)
@@ -734,6 +773,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 if (lane == 0) mbar_arrive(tempty_bar(ob.slot));   // all channels are in registers / stored, the slot is zero again
               }
               if (valid && !(DBG && (p.diag & 1))) {
+                uint4 ykeep = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                   float x[8], kc8[8];   // constants read at use (volatile: not hoisted into registers for the whole layer)
@@ -744,7 +784,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   if constexpr (HAS_SKIP) {
                     uint4 sv;   // 8 channels of the skip tensor at this position (plane 2 jj + hf)
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sv.x), "=r"(sv.y), "=r"(sv.z), "=r"(sv.w)
-                                 : "r"(sk_addr + (uint32_t)(2 * jj + hf) * sk_plane));
+                                 : "r"(k32 ? sk_addr32 + (uint32_t)jj * 4096u + (((uint32_t)hf ^ swl) << 4)
+                                           : sk_addr + (uint32_t)(2 * jj + hf) * sk_plane));
                     const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&sv);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -761,9 +802,16 @@ resnet_tc_sweep_kernel(const SwParams p) {
                     __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-                    uint4* dst = y_out + (int64_t)(2 * jj + hf) * plane_stride + ob.off;
-                    if (use_pol) st_hint(dst, yo, pol_out);
-                    else *dst = yo;
+                    if constexpr (k32) {
+                      // both halves of this row's 32 bytes in ONE store (16-byte stores at a 32-byte stride would write
+                      // every sector in two halves); which half comes first follows the row's swizzle bit
+                      if (hf == 0) ykeep = yo;
+                      else st_hint256(y_out + jj * kc_stride + ob.off, swl ? yo : ykeep, swl ? ykeep : yo, pol_out);
+                    } else {
+                      uint4* dst = y_out + (int64_t)(2 * jj + hf) * plane_stride + ob.off;
+                      if (use_pol) st_hint(dst, yo, pol_out);
+                      else *dst = yo;
+                    }
                   }
                 }
               }
@@ -782,7 +830,17 @@ resnet_tc_sweep_kernel(const SwParams p) {
           auto stage_skip = [&](const Own& ob) {
             if constexpr (HAS_SKIP) {
               asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");   // the group's four warps are done with the slot
-              if (packed) {
+              if (k32) {
+                if (q == 0 && ob.exists && elect_one()) {   // [K chunk][128 rows][32 B]
+                  const uint32_t bytes = (uint32_t)H * 32u;
+                  mbar_expect_tx(skfull_bar(g), bytes * NKC);
+                  const uint4* src = bufP + (int64_t)ob.w * H * 2;
+                  const uint32_t d0 = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT;
+#pragma unroll
+                  for (int kc = 0; kc < NKC; ++kc)
+                    bulk_load_hint(d0 + (uint32_t)kc * 4096u, src + kc * kc_stride, bytes, skfull_bar(g), pol_keep);
+                }
+              } else if (packed) {
                 if (q == 0 && ob.exists && elect_one()) {   // planes PP rows apart, one copy (host plan: PP <= 128)
                   const uint32_t bytes = (uint32_t)(NP * PP) * 16u;
                   mbar_expect_tx(skfull_bar(g), bytes);

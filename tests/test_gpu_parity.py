@@ -398,6 +398,27 @@ def test_bf16_column_sweep_kernel_matches_position_major_kernel_at_full_batch(de
     assert logit_err(ys[0][torch.from_numpy(idx).to(dev)].cpu().numpy(), ref) <= BF16_TOL
 
 
+@pytest.mark.parametrize("name", ["res15", "res15_narrow"])
+def test_bf16_sweep_kernel_planar_layout_matches_16_channel_row_layout(dev, monkeypatch, model_golden, name):
+    """The default activation layout for single-strip maps is [K chunk][w][h][16 channels] (swizzle-32B operand, one
+    bulk copy per K chunk, 32-byte stores); HONK2_TC_SWEEP_K32=0 selects the planar [8-channel plane][w][h] layout
+    that multi-strip maps use.  Same arithmetic: logits agree to accumulation-order noise, both with the golden."""
+    feats = torch.from_numpy(model_golden["feats"]).to(dev)
+    with torch.no_grad():
+        monkeypatch.setenv("HONK2_TC_SWEEP_K32", "0")
+        m_planar, _ = gpu_model(name, "hardened", dev, precision="bf16")
+        y_planar = m_planar(feats)
+        monkeypatch.setenv("HONK2_TC_SWEEP_K32", "1")
+        m_k32, _ = gpu_model(name, "hardened", dev, precision="bf16")
+        y_k32 = m_k32(feats)
+        y_again = m_k32(feats)
+    scale = float(y_planar.abs().max())
+    assert float((y_k32 - y_planar).abs().max()) <= 2e-3 * scale
+    assert float((y_k32 - y_again).abs().max()) <= 2e-3 * scale
+    assert logit_err(y_k32.cpu().numpy(), model_golden[f"{name}/hardened/logits"]) <= BF16_TOL
+    assert logit_err(y_planar.cpu().numpy(), model_golden[f"{name}/hardened/logits"]) <= BF16_TOL
+
+
 def test_bf16_sweep_kernel_packed_column_layout(dev, monkeypatch, model_golden):
     """HONK2_TC_SWEEP_PACKED=1 (opt-in): activations stored as whole columns with the zero padding rows in HBM, staged
     by one bulk copy per step.  Same arithmetic as the planar layout, so the logits must agree to accumulation-order
