@@ -882,14 +882,36 @@ resnet_tc_sweep_kernel(const SwParams p) {
       }
 
       // ------------------------------ logits (resnet.py:59) ------------------------------
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      for (int lb = et; lb < p.n_labels; lb += kEpiThreads) {
+      // One label per warp, lanes over the channels (C <= 64 on this kernel); the label's folded weights are fetched
+      // BEFORE the barrier, so their L2 latency overlaps the wait for the other warps' pooled sums.  (All epilogue
+      // warps stand at these two barriers between utterances while the accumulator ring fills up behind them: with
+      // one thread per label walking the channels through global loads the event trace showed a ~20 000-cycle stall
+      // per utterance, ~8 000 with this form.  Under the power cap the end-to-end gain is within noise.)
+      // s_pool holds sums of z = x - mean; the BatchNorm output mean is z_mean / sigma (resnet.py:55-58)
+      {
         const float inv = 1.f / (float)(H * W);
-        float v = __ldg(p.out_b + lb);
-        // s_pool holds sums of z = x - mean; the BatchNorm output mean is z_mean / sigma (resnet.py:55-58)
-        for (int c = 0; c < p.C; ++c)
-          v = fmaf(s_pool[c] * inv * __ldg(p.last_scale + c), __ldg(p.out_w + lb * p.C + c), v);
-        p.logits[b * p.n_labels + lb] = v;
+        auto fold = [&](int lb, float (&wv)[2]) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int c = lane + 32 * k;
+            wv[k] = c < p.C ? __ldg(p.last_scale + c) * inv * __ldg(p.out_w + lb * p.C + c) : 0.f;
+          }
+        };
+        float wv[2] = {0.f, 0.f};
+        if (warp < p.n_labels) fold(warp, wv);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        for (int lb = warp; lb < p.n_labels; lb += kEpiWarps) {
+          if (lb != warp) fold(lb, wv);
+          float v = 0.f;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int c = lane + 32 * k;
+            if (c < p.C) v = fmaf(s_pool[c], wv[k], v);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) p.logits[b * p.n_labels + lb] = v + __ldg(p.out_b + lb);
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (et < CP) s_pool[et] = 0.f;

@@ -469,6 +469,24 @@ def test_bf16_res15_hey_snips_shaped_clips(dev):
     assert logit_err(y, ref) <= BF16_TOL, logit_err(y, ref)
 
 
+@pytest.mark.parametrize("n_labels", [1, 35, 100])
+def test_bf16_sweep_kernel_label_counts(dev, n_labels, model_golden):
+    """The sweep kernel's tail computes one label per epilogue warp (12 warps for 45 maps): fewer labels than warps,
+    the 35 words of GSC v2 (three labels per warp), and many more; against the CPU oracle."""
+    kind, cfg = model_config("res15", n_labels=n_labels)
+    m = honk2_b200.build_model("res15", n_labels=n_labels, precision="bf16")
+    sd = m.state_dict()
+    synth.harden_(sd)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    x = torch.from_numpy(model_golden["feats"])
+    ref = model_ref.forward(kind, {k: v.clone() for k, v in sd.items()}, cfg, x).numpy()
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu().numpy()
+    assert y.shape == (x.shape[0], n_labels) and np.isfinite(y).all()
+    assert logit_err(y, ref) <= BF16_TOL, logit_err(y, ref)
+
+
 @pytest.mark.parametrize("T,F,B", [(100, 8, 5), (128, 3, 2), (129, 17, 3), (97, 1, 4)])
 def test_bf16_sweep_kernel_odd_map_shapes(dev, T, F, B):
     """Maps narrower than the dilation (every run is a single column: one-block windows, both stand-in arrivals),
