@@ -935,6 +935,7 @@ struct TcResNet {
   // column-sweep whole-network kernel (resnet_sweep.cuh), preferred when the map is tall enough
   bool sweep_enabled = true;
   bool sweep_k32 = true;       // HONK2_TC_SWEEP_K32=0 disables: 16-channel rows, swizzle-32B staging (single-strip maps)
+  bool sweep_colalign = false; // HONK2_TC_SWEEP_COLALIGN=1: planar columns start on 128-byte lines
   bool sweep_packed = false;   // HONK2_TC_SWEEP_PACKED=1: whole columns contiguous in HBM (one bulk copy per step; measured slower, see tc_sweep_plan)
   void* sweep_dev = nullptr;   // [SwLayerDesc x n_layers][pad][CUtensorMap x n_layers]
   std::tuple<int, int, const void*> sweep_key{-1, -1, nullptr};
@@ -1093,6 +1094,7 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
     p->sweep_enabled = senv == nullptr || std::atoi(senv) != 0;
     { const char* e = std::getenv("HONK2_TC_SWEEP_PACKED"); p->sweep_packed = e != nullptr && std::atoi(e) != 0; }
     { const char* e = std::getenv("HONK2_TC_SWEEP_K32"); p->sweep_k32 = e == nullptr || std::atoi(e) != 0; }
+    { const char* e = std::getenv("HONK2_TC_SWEEP_COLALIGN"); p->sweep_colalign = e != nullptr && std::atoi(e) != 0; }
     const char* env = std::getenv("HONK2_TC_LANES");
     p->lanes = env ? std::max(1, std::min(kTcMaxLanes, std::atoi(env))) : 2;
     bool ok = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) == cudaSuccess;
@@ -1410,8 +1412,7 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W) {
   f.packed = bulk_on && p->sweep_packed && f.n_strips == 1 && H + dmax <= 128;
   // planar layout: columns start on 128-byte lines (every line of a dead Q column can then be discarded from L2);
   // the TMA-box fallback keeps the dense pitch its tensor maps describe
-  static const bool col_align = [] { const char* e = std::getenv("HONK2_TC_SWEEP_COLALIGN"); return e != nullptr && std::atoi(e) != 0; }();
-  f.col_rows = (bulk_on && col_align) ? round_up(H, 8) : H;
+  f.col_rows = (bulk_on && p->sweep_colalign) ? round_up(H, 8) : H;
   // 16 channels per row (HONK2_TC_SWEEP_K32): [K chunk][w][h][32 B] in HBM, swizzle-32B operand in shared memory,
   // NKC bulk copies per step instead of 2*NKC (resnet_sweep.cuh)
   f.k32 = bulk_on && p->sweep_k32 && !f.packed && f.n_strips == 1;

@@ -419,6 +419,19 @@ def test_bf16_sweep_kernel_planar_layout_matches_16_channel_row_layout(dev, monk
     assert logit_err(y_planar.cpu().numpy(), model_golden[f"{name}/hardened/logits"]) <= BF16_TOL
 
 
+def test_bf16_sweep_kernel_line_aligned_planar_layout(dev, monkeypatch, model_golden):
+    """HONK2_TC_SWEEP_COLALIGN=1 with the planar layout (opt-in): columns padded to whole 128-byte lines."""
+    feats = torch.from_numpy(model_golden["feats"]).to(dev)
+    monkeypatch.setenv("HONK2_TC_SWEEP_K32", "0")
+    monkeypatch.setenv("HONK2_TC_SWEEP_COLALIGN", "1")
+    m, _ = gpu_model("res15", "hardened", dev, precision="bf16")
+    with torch.no_grad():
+        y = m(feats)
+        y2 = m(feats)
+    assert float((y - y2).abs().max()) <= 2e-3 * float(y.abs().max())
+    assert logit_err(y.cpu().numpy(), model_golden["res15/hardened/logits"]) <= BF16_TOL
+
+
 def test_bf16_sweep_kernel_packed_column_layout(dev, monkeypatch, model_golden):
     """HONK2_TC_SWEEP_PACKED=1 (opt-in): activations stored as whole columns with the zero padding rows in HBM, staged
     by one bulk copy per step.  Same arithmetic as the planar layout, so the logits must agree to accumulation-order
