@@ -5,9 +5,9 @@ import os
 
 from .build import LIB_PATH
 
-KWS_FP32, KWS_BF16 = 0, 1
-PRECISIONS = {"fp32": KWS_FP32, "bf16": KWS_BF16}
-ABI_VERSION = 1
+KWS_FP32, KWS_BF16, KWS_BF16X3 = 0, 1, 2
+PRECISIONS = {"fp32": KWS_FP32, "bf16": KWS_BF16, "bf16x3": KWS_BF16X3}
+ABI_VERSION = 2
 
 
 class NativeError(RuntimeError):
@@ -102,6 +102,11 @@ def load():
         raise NativeError(f"{path}: ABI version {lib.kws_abi_version()} != {ABI_VERSION}; rebuild")
     _lib = lib
     return lib
+
+
+def loaded():
+    """The library if it has already been loaded, else None (never triggers a load)."""
+    return _lib
 
 
 def check(status, what):

@@ -49,8 +49,8 @@ class AudioProcessor(object):
 
     def __del__(self):
         try:
-            lib = _native.load()
-            for h in self._handles.values():
+            lib = _native.loaded()   # (never dlopen from a destructor)
+            for h in (self._handles.values() if lib is not None else ()):
                 lib.kws_frontend_destroy(h)
         except Exception:
             pass

@@ -64,9 +64,19 @@ def find_cls(identifier, default_value=None):
     return _REGISTRY.get(identifier, default_value)
 
 
-def install_into(reference_register_cls):
+def install_into(reference_register_cls, prefixes=("model.",)):
     """Re-register this package's classes into ANOTHER registry (honk2's own
     ``utils.register_cls``) so that ``find_cls("model.ResNet")`` inside an unmodified honk2
-    checkout resolves to the B200 implementation (overwrite semantics, trie.py:21)."""
+    checkout resolves to the B200 implementation (overwrite semantics, trie.py:21).
+
+    Only the ``model.*`` identifiers are installed by default: ``run/run_utils.py`` is imported by
+    the training script too, and the device-resident metrics / loss of this package are inference
+    tools.  ``prefixes=("model.", "metric.", "loss_fn.", "data_loader.")`` opts in to the rest (they
+    keep the reference's ``get_type()`` / ``collect_metrics`` contract, metric/metric_utils.py:5-52).
+    Returns the identifiers it installed."""
+    done = []
     for ident in _REGISTRY.identifiers():
-        reference_register_cls(ident)(_REGISTRY.get(ident))
+        if any(ident.startswith(p) for p in prefixes):
+            reference_register_cls(ident)(_REGISTRY.get(ident))
+            done.append(ident)
+    return done

@@ -41,7 +41,9 @@ constexpr int kTcMaxMt = 8;       // upper bound of M-tiles per tile (min(8, kAc
 constexpr int kAccCols = 256;     // TMEM columns per accumulator buffer
 constexpr int kTcMaxLanes = 4;
 constexpr int kMaxStages = 8;
-constexpr long long kSpinLimitCycles = 4000000000ll;
+// Watchdog of the barrier waits: a protocol bug traps (kernel error) instead of hanging the GPU.  ~20 s of SM clocks:
+// far beyond any legitimate wait, generous enough for a time-sliced or profiled context.
+constexpr long long kSpinLimitCycles = 40000000000ll;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -91,11 +93,10 @@ __device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) 
 // Wait with few instructions per poll (for the MMA issuers, whose instruction count is the bottleneck): the
 // hardware suspends the thread until the phase completes or the hint elapses; the watchdog is read every 256 polls.
 // The hinted try_wait compiles to TRYWAIT + NANOSLEEP.SYNCS: the thread leaves the issue slots to other warps, but waking
-// up is slow; waits that are usually short poll a few times first (HONK2_TC_WAIT_POLLS, default 48; measured +2-4 %).
-__device__ int g_wait_polls;
-__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+// up is slow; waits that are usually short poll a few times first (`polls`, a kernel parameter: HONK2_TC_WAIT_POLLS,
+// default 48; measured +2-4 %).
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity, int polls) {
   if (mbar_try_wait(bar, parity)) return;
-  const int polls = g_wait_polls;
 #pragma unroll 1
   for (int i = 0; i < polls; ++i)
     if (mbar_try_wait(bar, parity)) return;
@@ -112,7 +113,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > kSpinLimitCycles) __trap();   // ~2 s: far beyond any legitimate wait
+    if (clock64() - t0 > kSpinLimitCycles) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
@@ -809,8 +810,9 @@ tail_p8_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ ou
 // torch [C][C][3][3] fp32 -> [9][NKC][2][CP][8] bf16 (tap, 16-ch chunk, K half, cout, 8 cin)
 // `in_scale` (nullable): BN scale 1/sigma of the PREVIOUS layer, folded into the input-channel axis
 // (exact: the convolution is linear and zero padding stays zero).
+// `out_lo` (nullable): the residual v - float(bf16(v)) in the same layout (the lo weight set of the split-bf16 mode).
 __global__ void pack_conv3x3_tc_kernel(const float* __restrict__ w, const float* __restrict__ in_scale,
-                                       __nv_bfloat16* __restrict__ out, int C, int NKC) {
+                                       __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, int C, int NKC) {
   const int CP = 16 * NKC;
   const int total = 9 * NKC * 2 * CP * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -823,7 +825,9 @@ __global__ void pack_conv3x3_tc_kernel(const float* __restrict__ w, const float*
     const int ci = kc * 16 + half * 8 + e;
     float v = (co < C && ci < C) ? w[((int64_t)co * C + ci) * 9 + tap] : 0.f;
     if (in_scale != nullptr && ci < C) v *= in_scale[ci];
-    out[i] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = hi;
+    if (out_lo != nullptr) out_lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
 }
 
@@ -831,7 +835,7 @@ __global__ void pack_conv3x3_tc_kernel(const float* __restrict__ w, const float*
 // (resnet_sweep.cuh): block k of a (16-channel chunk, height tap) slab holds the width tap dw = 2 - k, so that
 // one N = 3*CP MMA on input column w feeds output columns w-d, w, w+d.  `in_scale` as above.
 __global__ void pack_conv3x3_sw_kernel(const float* __restrict__ w, const float* __restrict__ in_scale,
-                                       __nv_bfloat16* __restrict__ out, int C, int NKC) {
+                                       __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, int C, int NKC) {
   const int CP = 16 * NKC;
   const int total = NKC * 3 * 2 * 3 * CP * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -846,14 +850,17 @@ __global__ void pack_conv3x3_sw_kernel(const float* __restrict__ w, const float*
     const int tap = dh * 3 + (2 - blk);
     float v = (co < C && ci < C) ? w[((int64_t)co * C + ci) * 9 + tap] : 0.f;
     if (in_scale != nullptr && ci < C) v *= in_scale[ci];
-    out[i] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[i] = hi;
+    if (out_lo != nullptr) out_lo[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
 }
 
 // conv_0 weights [C][1][3][3] fp32 -> one-chunk sweep slab set [3 dh][2 K halves][3 blocks][CP][8] bf16: the staged
 // "activation" of the conv_0 pseudo-layer carries the bf16 high and low parts of the feature in channels 0 and 1, so
-// the weight sits in both positions (k = 0, 1 of K half 0) and everything else is zero.
-__global__ void pack_conv0_sw_kernel(const float* __restrict__ w0, __nv_bfloat16* __restrict__ out, int C, int CP) {
+// the weight sits in both positions (k = 0, 1 of K half 0) and everything else is zero.  split != 0 (bf16x3): channel 2
+// carries the feature's high part again and k = 2 holds the weight's residual w - float(bf16(w)).
+__global__ void pack_conv0_sw_kernel(const float* __restrict__ w0, __nv_bfloat16* __restrict__ out, int C, int CP, int split) {
   const int total = 3 * 2 * 3 * CP * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 7;
@@ -863,8 +870,9 @@ __global__ void pack_conv0_sw_kernel(const float* __restrict__ w0, __nv_bfloat16
     const int half = t & 1; t >>= 1;
     const int dh = t;
     const int tap = dh * 3 + (2 - blk);
-    const float v = (half == 0 && e < 2 && co < C) ? w0[co * 9 + tap] : 0.f;
-    out[i] = __float2bfloat16_rn(v);
+    const float w = (half == 0 && e < 3 && co < C) ? w0[co * 9 + tap] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    out[i] = e < 2 ? hi : (split && e == 2) ? __float2bfloat16_rn(w - __bfloat162float(hi)) : __float2bfloat16_rn(0.f);
   }
 }
 
@@ -917,11 +925,13 @@ struct TcResNet {
   bool supported = false;
   int n_sms = 148;
   void* blob = nullptr;
-  std::vector<__nv_bfloat16*> wpack;        // per layer
-  std::vector<__nv_bfloat16*> wpack_sw;     // per layer, column-sweep layout (resnet_sweep.cuh)
+  // per layer; every packed weight array is [hi set][lo set] (the lo set = residuals, read by the split-bf16 mode only)
+  std::vector<__nv_bfloat16*> wpack;        // position-major layout
+  std::vector<__nv_bfloat16*> wpack_sw;     // column-sweep layout (resnet_sweep.cuh)
   std::vector<float*> scale_p, shift_p;     // per layer, padded to CP: BN 1/sigma and the epilogue constant
   float* conv0_w = nullptr;                 // [C][9]
   __nv_bfloat16* conv0_wb = nullptr;        // conv_0 as a one-chunk sweep slab set (pack_conv0_sw_kernel)
+  __nv_bfloat16* conv0_wb3 = nullptr;       // same for the split-bf16 mode
   float* out_w = nullptr;
   float* out_b = nullptr;
   std::map<std::tuple<const void*, int64_t, int, int, int>, CUtensorMap> maps;
@@ -929,18 +939,14 @@ struct TcResNet {
   // rebuilt when the input shape or the workspace changes
   bool fused_enabled = true;
   void* fused_dev = nullptr;   // [TcLayerDesc x n_layers][pad][CUtensorMap x n_layers]
-  std::tuple<int, int, const void*> fused_key{-1, -1, nullptr};
+  std::tuple<int, int, const void*, int> fused_key{-1, -1, nullptr, 0};
   TcFusedParams fused_prm{};
   int fused_smem = 0;
   // column-sweep whole-network kernel (resnet_sweep.cuh), preferred when the map is tall enough
   bool sweep_enabled = true;
-  bool sweep_k32 = true;       // HONK2_TC_SWEEP_K32=0 disables: 16-channel rows, swizzle-32B staging (single-strip maps)
-  bool sweep_colalign = false; // HONK2_TC_SWEEP_COLALIGN=1: planar columns start on 128-byte lines
-  bool sweep_packed = false;   // HONK2_TC_SWEEP_PACKED=1: whole columns contiguous in HBM (one bulk copy per step; measured slower, see tc_sweep_plan)
-  void* sweep_dev = nullptr;   // [SwLayerDesc x n_layers][pad][CUtensorMap x n_layers]
-  std::tuple<int, int, const void*> sweep_key{-1, -1, nullptr};
-  SwParams sweep_prm{};
-  int sweep_smem = 0;
+  bool sweep_k32 = true;       // HONK2_TC_SWEEP_K32=0: single-strip maps use the planar layout of the multi-strip maps too
+  int l2_policy = 1, wait_polls = 48, sweep_max_stages = 0, sweep_min_pct = 60;
+  bool sweep_discard = true;
   // chunk pipelining: consecutive chunks run on `lanes` internal streams so that the prologue / tail of one
   // chunk's layer kernels overlaps the steady state of another's (each lane has its own activation buffers)
   int lanes = 1;
@@ -1067,10 +1073,11 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
   cudaDeviceGetAttribute(&p->n_sms, cudaDevAttrMultiProcessorCount, dev);
   if (p->supported) {
     const int n = cfg.n_layers;
-    const size_t w_bytes = round_up<size_t>((size_t)9 * p->NKC * 2 * p->CP * 16, 256);
+    // one weight set is a multiple of 256 bytes (CP is a multiple of 16), so [hi set][lo set] is contiguous
+    const size_t w_bytes = 2 * (size_t)9 * p->NKC * 2 * p->CP * 16;
     const size_t v_bytes = round_up<size_t>(p->CP * sizeof(float), 256);
     const size_t c0_bytes = round_up<size_t>((size_t)3 * 2 * 3 * p->CP * 16, 256);
-    const size_t total = n * (2 * w_bytes + 2 * v_bytes) + c0_bytes + round_up<size_t>(C * 9 * 4, 256) +
+    const size_t total = n * (2 * w_bytes + 2 * v_bytes) + 2 * c0_bytes + round_up<size_t>(C * 9 * 4, 256) +
                          round_up<size_t>((size_t)cfg.n_labels * C * 4, 256) + round_up<size_t>(cfg.n_labels * 4, 256);
     if (cudaMalloc(&p->blob, total) != cudaSuccess) {
       set_error("tc_resnet_create: cudaMalloc(%zu) failed", total);
@@ -1085,18 +1092,21 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
       p->shift_p.push_back(reinterpret_cast<float*>(b)); b += v_bytes;
     }
     p->conv0_wb = reinterpret_cast<__nv_bfloat16*>(b); b += c0_bytes;
+    p->conv0_wb3 = reinterpret_cast<__nv_bfloat16*>(b); b += c0_bytes;
     p->conv0_w = reinterpret_cast<float*>(b); b += round_up<size_t>(C * 9 * 4, 256);
     p->out_w = reinterpret_cast<float*>(b); b += round_up<size_t>((size_t)cfg.n_labels * C * 4, 256);
     p->out_b = reinterpret_cast<float*>(b);
-    const char* fenv = std::getenv("HONK2_TC_FUSED");
-    p->fused_enabled = fenv == nullptr || std::atoi(fenv) != 0;
-    const char* senv = std::getenv("HONK2_TC_SWEEP");
-    p->sweep_enabled = senv == nullptr || std::atoi(senv) != 0;
-    { const char* e = std::getenv("HONK2_TC_SWEEP_PACKED"); p->sweep_packed = e != nullptr && std::atoi(e) != 0; }
-    { const char* e = std::getenv("HONK2_TC_SWEEP_K32"); p->sweep_k32 = e == nullptr || std::atoi(e) != 0; }
-    { const char* e = std::getenv("HONK2_TC_SWEEP_COLALIGN"); p->sweep_colalign = e != nullptr && std::atoi(e) != 0; }
-    const char* env = std::getenv("HONK2_TC_LANES");
-    p->lanes = env ? std::max(1, std::min(kTcMaxLanes, std::atoi(env))) : 2;
+    // every knob is read HERE, once per model handle (DESIGN.md section 4 lists them)
+    auto env_int = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
+    p->fused_enabled = env_int("HONK2_TC_FUSED", 1) != 0;
+    p->sweep_enabled = env_int("HONK2_TC_SWEEP", 1) != 0;
+    p->sweep_k32 = env_int("HONK2_TC_SWEEP_K32", 1) != 0;
+    p->sweep_discard = env_int("HONK2_TC_SWEEP_DISCARD", 1) != 0;
+    p->sweep_max_stages = env_int("HONK2_TC_SWEEP_STAGES", kSwMaxStages);
+    p->sweep_min_pct = env_int("HONK2_TC_SWEEP_MINPCT", 60);
+    p->l2_policy = env_int("HONK2_TC_L2POLICY", 1);
+    p->wait_polls = env_int("HONK2_TC_WAIT_POLLS", 48);
+    p->lanes = std::max(1, std::min(kTcMaxLanes, env_int("HONK2_TC_LANES", 2)));
     bool ok = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming) == cudaSuccess;
     for (int l = 0; l < p->lanes && ok; ++l)
       ok = cudaStreamCreateWithFlags(&p->lane_stream[l], cudaStreamNonBlocking) == cudaSuccess &&
@@ -1115,7 +1125,6 @@ void tc_resnet_destroy(TcResNet* p) {
   if (!p) return;
   if (p->blob) cudaFree(p->blob);
   if (p->fused_dev) cudaFree(p->fused_dev);
-  if (p->sweep_dev) cudaFree(p->sweep_dev);
   for (int l = 0; l < kTcMaxLanes; ++l) {
     if (p->lane_stream[l]) cudaStreamDestroy(p->lane_stream[l]);
     if (p->ev_done[l]) cudaEventDestroy(p->ev_done[l]);
@@ -1129,11 +1138,12 @@ int tc_resnet_set_weights(TcResNet* p, const kws_resnet_weights& w, float* const
   if (!p->supported) return KWS_OK;
   const int C = p->cfg.n_maps, n = p->cfg.n_layers, L = p->cfg.n_labels;
   for (int i = 0; i < n; ++i) {
-    pack_conv3x3_tc_kernel<<<ceil_div(9 * p->NKC * 2 * p->CP * 8, 256), 256, 0, st>>>(
-        w.conv_w[i], i > 0 ? bn_scale[i - 1] : nullptr, p->wpack[i], C, p->NKC);
+    const int set_elems = 9 * p->NKC * 2 * p->CP * 8;   // one weight set; the lo set follows it
+    pack_conv3x3_tc_kernel<<<ceil_div(set_elems, 256), 256, 0, st>>>(
+        w.conv_w[i], i > 0 ? bn_scale[i - 1] : nullptr, p->wpack[i], p->wpack[i] + set_elems, C, p->NKC);
     KWS_CUDA(cudaGetLastError());
-    pack_conv3x3_sw_kernel<<<ceil_div(9 * p->NKC * 2 * p->CP * 8, 256), 256, 0, st>>>(
-        w.conv_w[i], i > 0 ? bn_scale[i - 1] : nullptr, p->wpack_sw[i], C, p->NKC);
+    pack_conv3x3_sw_kernel<<<ceil_div(set_elems, 256), 256, 0, st>>>(
+        w.conv_w[i], i > 0 ? bn_scale[i - 1] : nullptr, p->wpack_sw[i], p->wpack_sw[i] + set_elems, C, p->NKC);
     KWS_CUDA(cudaGetLastError());
     // layer number i+1 is even and > 2  <=>  its skip comes from a normalised layer (i-1 in 0-based terms)
     const float* skip_mean = ((i + 1) % 2 == 0 && i >= 3) ? w.bn_mean[i - 2] : nullptr;
@@ -1141,7 +1151,9 @@ int tc_resnet_set_weights(TcResNet* p, const kws_resnet_weights& w, float* const
     KWS_CUDA(cudaGetLastError());
   }
   KWS_CUDA(cudaMemcpyAsync(p->conv0_w, w.conv0_w, sizeof(float) * C * 9, cudaMemcpyDeviceToDevice, st));
-  pack_conv0_sw_kernel<<<ceil_div(3 * 2 * 3 * p->CP * 8, 256), 256, 0, st>>>(w.conv0_w, p->conv0_wb, C, p->CP);
+  pack_conv0_sw_kernel<<<ceil_div(3 * 2 * 3 * p->CP * 8, 256), 256, 0, st>>>(w.conv0_w, p->conv0_wb, C, p->CP, 0);
+  KWS_CUDA(cudaGetLastError());
+  pack_conv0_sw_kernel<<<ceil_div(3 * 2 * 3 * p->CP * 8, 256), 256, 0, st>>>(w.conv0_w, p->conv0_wb3, C, p->CP, 1);
   KWS_CUDA(cudaGetLastError());
   KWS_CUDA(cudaMemcpyAsync(p->out_w, w.out_w, sizeof(float) * L * C, cudaMemcpyDeviceToDevice, st));
   KWS_CUDA(cudaMemcpyAsync(p->out_b, w.out_b, sizeof(float) * L, cudaMemcpyDeviceToDevice, st));
@@ -1231,25 +1243,27 @@ static int tc_encode_map(const void* base, int64_t planes, int H, int W, const T
 
 // ---- whole-network persistent kernel: geometry, shared-memory plan, device tables ----------------
 struct TcFusedPlan {
-  bool ok = false;
+  bool ok = false, split = false;
   int Hpad = 0, n_slots = 0, smem_total = 0;
   int w_off[2] = {0, 0}, ring_off = 0, slot_bytes = 0;
   std::vector<TcGeom> geoms;
 };
 
-static TcFusedPlan tc_fused_plan(const TcResNet* p, int H, int W) {
+static TcFusedPlan tc_fused_plan(const TcResNet* p, int H, int W, bool split) {
   TcFusedPlan f;
   const kws_resnet_config& c = p->cfg;
-  if (!p->fused_enabled || c.n_layers < 1 || c.n_layers > kFusedMaxLayers || c.n_labels > 4096) return f;
+  if ((!p->fused_enabled && !split) || c.n_layers < 1 || c.n_layers > kFusedMaxLayers || c.n_labels > 4096) return f;
   f.Hpad = tc_hpad(c, H);
   f.n_slots = p->n_sms;
-  const int w_bytes = 9 * p->NKC * 2 * p->CP * 16;
+  f.split = split;
+  const int w_bytes = (split ? 2 : 1) * 9 * p->NKC * 2 * p->CP * 16;
   f.w_off[0] = 5120;   // control block: barriers, pooled sums, constants, layer descriptors, conv_0 weights
-  f.w_off[1] = f.w_off[0] + round_up(w_bytes, 128);
+  f.w_off[1] = split ? f.w_off[0] : f.w_off[0] + round_up(w_bytes, 128);   // (split: one buffer for both weight sets)
   f.ring_off = round_up(f.w_off[1] + w_bytes, 1024);
   for (int i = 1; i <= c.n_layers; ++i) {
     TcGeom g;
     const int d = c.use_dilation ? (1 << ((i - 1) / 3)) : 1;
+    // (tc_geom sizes its tiles for the layer-per-launch kernel's shared memory; the check below is this kernel's)
     if (!tc_geom(p->NKC, H, f.Hpad, W, d, &g)) return f;
     f.slot_bytes = std::max(f.slot_bytes, round_up(g.stage_bytes, 128));
     f.geoms.push_back(g);
@@ -1260,17 +1274,21 @@ static TcFusedPlan tc_fused_plan(const TcResNet* p, int H, int W) {
 }
 
 static size_t tc_fused_ws_bytes(const TcResNet* p, const TcFusedPlan& f, int W, size_t* buf_out) {
-  const size_t buf = round_up<size_t>((size_t)f.n_slots * p->NP * f.Hpad * W * 16, 1024);
+  const size_t buf = round_up<size_t>((size_t)f.n_slots * (f.split ? 2 : 1) * p->NP * f.Hpad * W * 16, 1024);
   if (buf_out) *buf_out = buf;
   return 2 * buf;
 }
 
-template <int NKC>
-static int tc_launch_fused(const TcFusedParams& prm, int grid, int smem, cudaStream_t st) {
-  KWS_CUDA(cudaFuncSetAttribute(resnet_tc_fused_kernel<NKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  resnet_tc_fused_kernel<NKC><<<grid, tc_threads(NKC), smem, st>>>(prm);
+template <int NKC, bool SPLIT>
+static int tc_launch_fused_v(const TcFusedParams& prm, int grid, int smem, cudaStream_t st) {
+  KWS_CUDA(cudaFuncSetAttribute(resnet_tc_fused_kernel<NKC, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  resnet_tc_fused_kernel<NKC, SPLIT><<<grid, tc_threads(NKC), smem, st>>>(prm);
   KWS_CHECK_LAUNCH();
   return KWS_OK;
+}
+template <int NKC>
+static int tc_launch_fused(const TcFusedParams& prm, bool split, int grid, int smem, cudaStream_t st) {
+  return split ? tc_launch_fused_v<NKC, true>(prm, grid, smem, st) : tc_launch_fused_v<NKC, false>(prm, grid, smem, st);
 }
 
 static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat, int64_t B, int T, int F, int H, int W,
@@ -1280,7 +1298,7 @@ static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat
   tc_fused_ws_bytes(p, f, W, &buf);
   __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws));
   __nv_bfloat16* Q = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + buf);
-  const auto key = std::make_tuple(T, F, (const void*)ws);
+  const auto key = std::make_tuple(T, F, (const void*)ws, f.split ? 1 : 0);
   if (p->fused_key != key) {
     // (re)build the device tables: layer descriptors + one input tensor map per layer
     const int n = c.n_layers;
@@ -1297,7 +1315,7 @@ static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat
       L.last = (i == n) ? 1 : 0;
       memcpy(host.data() + sizeof(TcLayerDesc) * (i - 1), &L, sizeof(L));
       CUtensorMap m;
-      KWS_TRY(tc_encode_map(L.in_buf ? Q : P, (int64_t)f.n_slots * p->NP, H, W, L.g, &m));
+      KWS_TRY(tc_encode_map(L.in_buf ? Q : P, (int64_t)f.n_slots * (f.split ? 2 : 1) * p->NP, H, W, L.g, &m));
       memcpy(host.data() + maps_off + sizeof(CUtensorMap) * (i - 1), &m, sizeof(m));
     }
     if (p->fused_dev) { KWS_CUDA(cudaStreamSynchronize(st)); KWS_CUDA(cudaFree(p->fused_dev)); p->fused_dev = nullptr; }
@@ -1318,17 +1336,14 @@ static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat
     q.H = H; q.W = W; q.Hpad = f.Hpad;
     q.smem_w_off[0] = f.w_off[0]; q.smem_w_off[1] = f.w_off[1];
     q.smem_ring_off = f.ring_off; q.ring_slot_bytes = f.slot_bytes;
-    {
-      const char* e = std::getenv("HONK2_TC_L2POLICY");
-      q.l2_policy = e ? std::atoi(e) : 1;
-    }
+    q.l2_policy = p->l2_policy;
     p->fused_smem = f.smem_total;
     p->fused_key = key;
   }
   if (prof) prof->tick(1, st);
   if (f.Hpad > H) {
     for (__nv_bfloat16* bp : {P, Q}) {
-      zero_pad_rows_kernel<<<256, 256, 0, st>>>(reinterpret_cast<uint4*>(bp), (int64_t)f.n_slots * p->NP, H, f.Hpad, W);
+      zero_pad_rows_kernel<<<256, 256, 0, st>>>(reinterpret_cast<uint4*>(bp), (int64_t)f.n_slots * (f.split ? 2 : 1) * p->NP, H, f.Hpad, W);
       KWS_CHECK_LAUNCH();
     }
   }
@@ -1358,24 +1373,23 @@ static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat
     }
   } dbg_print{dbg_on ? dbg_buf : nullptr, st};
   switch (p->NKC) {
-    case 1: return tc_launch_fused<1>(prm, grid, p->fused_smem, st);
-    case 2: return tc_launch_fused<2>(prm, grid, p->fused_smem, st);
-    case 3: return tc_launch_fused<3>(prm, grid, p->fused_smem, st);
-    default: return tc_launch_fused<4>(prm, grid, p->fused_smem, st);
+    case 1: return tc_launch_fused<1>(prm, f.split, grid, p->fused_smem, st);
+    case 2: return tc_launch_fused<2>(prm, f.split, grid, p->fused_smem, st);
+    case 3: return tc_launch_fused<3>(prm, f.split, grid, p->fused_smem, st);
+    default: return tc_launch_fused<4>(prm, f.split, grid, p->fused_smem, st);
   }
 }
 
-// ---- column-sweep whole-network kernel (resnet_sweep.cuh): plan, tables, launch --------------------
+// ---- column-sweep whole-network kernel (resnet_sweep.cuh): plan, launch ------------------------------
 struct TcSweepPlan {
   bool ok = false;
   int n_slots = 0, n_strips = 0, smem_total = 0, n_stages = 0;
-  int c0w_off = 0, w_off[2] = {0, 0}, skip_off = 0, ring_off = 0, slot_bytes = 0;
-  int dmax = 1, col_rows = 0;
-  bool bulk = false, packed = false, k32 = false;   // staging by bulk copies; whole columns contiguous in HBM (resnet_sweep.cuh)
-  std::vector<int> dil;
+  int c0w_off = 0, w_off[2] = {0, 0}, skip_off = 0, ring_off = 0, slot_bytes = 0, slack_bytes = 0;
+  int dmax = 1, chunk_rows = 0;
+  bool k32 = false, split = false;
 };
 
-static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W) {
+static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W, bool split) {
   TcSweepPlan f;
   const kws_resnet_config& c = p->cfg;
   if (!p->sweep_enabled || c.n_layers < 1 || c.n_layers > kFusedMaxLayers || c.n_labels > 4096) return f;
@@ -1386,72 +1400,61 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W) {
   f.n_strips = ceil_div(H, 128);
   // the 128 lanes of an MMA are 128 rows of one column: short maps (res8 / res26 after pooling) would leave
   // most lanes idle and stay on the position-major kernel
-  static const int min_pct = [] { const char* e = std::getenv("HONK2_TC_SWEEP_MINPCT"); return e ? std::atoi(e) : 60; }();
-  if (H * 100 < f.n_strips * 128 * min_pct) return f;
+  if (H * 100 < f.n_strips * 128 * p->sweep_min_pct) return f;
   int dmax = 1;
   for (int i = 1; i <= c.n_layers; ++i) {
     const int d = c.use_dilation ? (1 << ((i - 1) / 3)) : 1;
-    if (d > 64) return f;   // TMA box of 128 + 2d rows must stay <= 256
+    if (d > 64) return f;   // (a staged column of 128 + 2d rows per plane would no longer leave room for three stages)
     dmax = std::max(dmax, d);
-    f.dil.push_back(d);
   }
   f.n_slots = p->n_sms;
-  const int w_bytes = 9 * p->NKC * 2 * p->CP * 16;
+  f.dmax = dmax;
+  f.split = split;
+  // 16 channels per row: [K chunk][w][h][32 B] in HBM, swizzle-32B operand in shared memory, one bulk copy per chunk
+  // and step (single-strip maps; HONK2_TC_SWEEP_K32=0 keeps them on the planar layout of the multi-strip maps)
+  f.k32 = f.n_strips == 1 && (p->sweep_k32 || split);
+  if (split && !f.k32) return f;   // the split-bf16 mode is built on the 32-byte-row layout
+  const int set_bytes = 9 * p->NKC * 2 * p->CP * 16;           // one weight set
+  const int w_bytes = (split ? 2 : 1) * set_bytes;
   f.c0w_off = kSwCtrlBytes;
   f.w_off[0] = f.c0w_off + round_up(3 * 2 * 3 * p->CP * 16, 128);
-  f.w_off[1] = f.w_off[0] + round_up(w_bytes, 128);
+  f.w_off[1] = split ? f.w_off[0] : f.w_off[0] + round_up(w_bytes, 128);   // (split: one buffer, see the kernel)
   f.skip_off = round_up(f.w_off[1] + w_bytes, 1024);
-  f.ring_off = f.skip_off + p->NKC * p->NP * 2048;   // one skip slot per epilogue warp group
-  f.dmax = dmax;
-  static const bool bulk_on = [] { const char* e = std::getenv("HONK2_TC_SWEEP_BULK"); return e == nullptr || std::atoi(e) != 0; }();
-  f.bulk = bulk_on;
-  // Packed columns (opt-in): single strip, and plane pitch H + dmax <= 128 rows so that a skip column fits its 128-row
-  // slot.  One bulk copy per step instead of NP relieves the producer warp (+7 % when probed with a same-size single
-  // copy on the planar layout), but the zero rows between planes make the activations 18 % larger (res15: 136 MB for
-  // 148 CTAs against the 126 MB L2) and the whole kernel measured 4 % SLOWER (18.6 vs 17.8 ms), so planar stays the default.
-  f.packed = bulk_on && p->sweep_packed && f.n_strips == 1 && H + dmax <= 128;
-  // planar layout: columns start on 128-byte lines (every line of a dead Q column can then be discarded from L2);
-  // the TMA-box fallback keeps the dense pitch its tensor maps describe
-  f.col_rows = (bulk_on && p->sweep_colalign) ? round_up(H, 8) : H;
-  // 16 channels per row (HONK2_TC_SWEEP_K32): [K chunk][w][h][32 B] in HBM, swizzle-32B operand in shared memory,
-  // NKC bulk copies per step instead of 2*NKC (resnet_sweep.cuh)
-  f.k32 = bulk_on && p->sweep_k32 && !f.packed && f.n_strips == 1;
-  if (f.k32) f.col_rows = H;
-  int slack = 0;
-  if (f.packed) {
-    f.slot_bytes = round_up((p->NP * (H + dmax) + dmax) * 16, 128);
-    slack = 2048;   // the 128-row MMA operand of the last plane of the last stage reaches (128 - H) rows past its slot
-  } else {
-    f.slot_bytes = round_up(p->NP * ((128 + 2 * dmax + 7) & ~7) * 16, 128);
-  }
-  static const int max_stages = [] { const char* e = std::getenv("HONK2_TC_SWEEP_STAGES"); return e ? std::atoi(e) : kSwMaxStages; }();
-  f.n_stages = std::min(std::min(kSwMaxStages, max_stages), (227 * 1024 - slack - f.ring_off) / f.slot_bytes);
+  f.ring_off = f.skip_off + (split ? 0 : p->NKC * p->NP * 2048);   // one skip slot per epilogue warp group
+  // rows per chunk of a staged column.  The split mode stages twice the chunks: its chunks are cut down to the rows
+  // the map's own lanes read (H + 2 dmax); the lanes past the map then read into the next chunk / the slack.
+  const int full_rows = (128 + 2 * dmax + 7) & ~7;
+  f.chunk_rows = (split && f.n_strips == 1) ? std::min(full_rows, round_up(H + 2 * dmax, 8)) : full_rows;
+  f.slot_bytes = (split ? 2 : 1) * p->NP * f.chunk_rows * 16;
+  f.slack_bytes = (full_rows - f.chunk_rows) * 32;
+  const int max_stages = std::min(kSwMaxStages, p->sweep_max_stages > 0 ? p->sweep_max_stages : kSwMaxStages);
+  f.n_stages = std::min(max_stages, (227 * 1024 - f.slack_bytes - f.ring_off) / f.slot_bytes);
   if (f.n_stages < 3) return f;
-  f.smem_total = f.ring_off + f.n_stages * f.slot_bytes + slack;
+  f.smem_total = f.ring_off + f.n_stages * f.slot_bytes + f.slack_bytes;
   f.ok = true;
   return f;
 }
 
 static size_t tc_sweep_ws_bytes(const TcResNet* p, const TcSweepPlan& f, int H, int W, size_t* buf_out) {
-  const size_t col_rows = f.packed ? (size_t)p->NP * (H + f.dmax) + f.dmax : (size_t)p->NP * f.col_rows;
-  const size_t buf = round_up<size_t>((size_t)f.n_slots * col_rows * W * 16, 1024);
+  const size_t buf = round_up<size_t>((size_t)f.n_slots * (f.split ? 2 : 1) * p->NP * H * W * 16, 1024);
   if (buf_out) *buf_out = buf;
   return 2 * buf;
 }
 
-template <int NKC, bool DBG, bool K32>
+template <int NKC, bool DBG, bool K32, bool SPLIT>
 static int tc_launch_sweep_v(const SwParams& prm, int grid, int smem, cudaStream_t st) {
-  KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC, DBG, K32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  resnet_tc_sweep_kernel<NKC, DBG, K32><<<grid, sw_threads(NKC), smem, st>>>(prm);
+  KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC, DBG, K32, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  resnet_tc_sweep_kernel<NKC, DBG, K32, SPLIT><<<grid, sw_threads(NKC), smem, st>>>(prm);
   KWS_CHECK_LAUNCH();
   return KWS_OK;
 }
 
 template <int NKC>
-static int tc_launch_sweep(const SwParams& prm, int grid, int smem, cudaStream_t st) {
+static int tc_launch_sweep(const SwParams& prm, bool split, int grid, int smem, cudaStream_t st) {
+  if (split) return tc_launch_sweep_v<NKC, false, true, true>(prm, grid, smem, st);
   if (prm.debug != nullptr)
-    return prm.k32 ? tc_launch_sweep_v<NKC, true, true>(prm, grid, smem, st) : tc_launch_sweep_v<NKC, true, false>(prm, grid, smem, st);
-  return prm.k32 ? tc_launch_sweep_v<NKC, false, true>(prm, grid, smem, st) : tc_launch_sweep_v<NKC, false, false>(prm, grid, smem, st);
+    return prm.k32 ? tc_launch_sweep_v<NKC, true, true, false>(prm, grid, smem, st) : tc_launch_sweep_v<NKC, true, false, false>(prm, grid, smem, st);
+  return prm.k32 ? tc_launch_sweep_v<NKC, false, true, false>(prm, grid, smem, st) : tc_launch_sweep_v<NKC, false, false, false>(prm, grid, smem, st);
 }
 
 static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat, int64_t B, int T, int F, int H, int W,
@@ -1459,92 +1462,49 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
   const kws_resnet_config& c = p->cfg;
   size_t buf = 0;
   tc_sweep_ws_bytes(p, f, H, W, &buf);
-  __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws));
-  __nv_bfloat16* Q = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + buf);
-  const auto key = std::make_tuple(T, F, (const void*)ws);
-  if (p->sweep_key != key) {
-    const int n = c.n_layers;
-    const size_t maps_off = 0;
-    const size_t total = sizeof(CUtensorMap) * n;
-    std::vector<unsigned char> host(total, 0);
-    for (int i = 1; i <= n; ++i) {
-      const int d = f.dil[i - 1];
-      const int box_rows = (128 + 2 * d + 7) & ~7;
-      const bool in_q = (i % 2 == 0);
-      // dims: 8 channels, H rows, W columns, planes; box: {8, 128 + 2d rows, 1 column, NP planes}
-      CUtensorMap m;
-      const cuuint64_t dims[4] = {8, (cuuint64_t)H, (cuuint64_t)W, (cuuint64_t)f.n_slots * p->NP};
-      const cuuint64_t strides[3] = {16, (cuuint64_t)H * 16, (cuuint64_t)H * W * 16};
-      const cuuint32_t box[4] = {8, (cuuint32_t)box_rows, 1, (cuuint32_t)p->NP};
-      const cuuint32_t estr[4] = {1, 1, 1, 1};
-      CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, in_q ? (void*)Q : (void*)P, dims, strides, box,
-                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) for the column-sweep map H=%d W=%d box_rows=%d", (int)r, H, W, box_rows);
-        return KWS_ERR_CUDA;
-      }
-      memcpy(host.data() + maps_off + sizeof(CUtensorMap) * (i - 1), &m, sizeof(m));
-    }
-    if (p->sweep_dev) { KWS_CUDA(cudaStreamSynchronize(st)); KWS_CUDA(cudaFree(p->sweep_dev)); p->sweep_dev = nullptr; }
-    KWS_CUDA(cudaMalloc(&p->sweep_dev, total));
-    KWS_CUDA(cudaMemcpyAsync(p->sweep_dev, host.data(), total, cudaMemcpyHostToDevice, st));
-    KWS_CUDA(cudaStreamSynchronize(st));   // `host` goes out of scope; this happens once per shape
-    SwParams& q = p->sweep_prm;
-    q = SwParams{};
-    q.maps = reinterpret_cast<const CUtensorMap*>(static_cast<char*>(p->sweep_dev) + maps_off);
-    q.wpack0 = reinterpret_cast<const unsigned char*>(p->wpack_sw[0]);
-    q.kconst0 = reinterpret_cast<const unsigned char*>(p->shift_p[0]);
-    q.layer_stride = n > 1 ? (int64_t)(reinterpret_cast<const unsigned char*>(p->wpack_sw[1]) - q.wpack0) : 0;
-    q.use_dilation = c.use_dilation ? 1 : 0;
-    q.conv0_wb = reinterpret_cast<const unsigned char*>(p->conv0_wb);
-    q.last_scale = p->scale_p[n - 1];
-    q.out_w = p->out_w;
-    q.out_b = p->out_b;
-    q.P = P; q.Q = Q;
-    q.n_layers = n; q.C = c.n_maps; q.n_labels = c.n_labels; q.T = T; q.F = F;
-    q.H = H; q.W = W; q.n_strips = f.n_strips;
-    q.smem_c0w_off = f.c0w_off;
-    q.smem_skip_off = f.skip_off;
-    q.dmax = f.dmax;
-    q.bulk_rows = f.bulk ? H : 0;
-    q.packed = f.packed ? 1 : 0;
-    q.col_rows = f.col_rows;
-    q.k32 = f.k32 ? 1 : 0;
-    {
-      const char* e = std::getenv("HONK2_TC_SWEEP_DISCARD");
-      q.discard_q = (e ? std::atoi(e) != 0 : true) && f.n_strips == 1;
-    }
-    q.smem_w_off[0] = f.w_off[0]; q.smem_w_off[1] = f.w_off[1];
-    q.smem_ring_off = f.ring_off; q.ring_slot_bytes = f.slot_bytes; q.n_stages = f.n_stages;
-    {
-      const char* e = std::getenv("HONK2_TC_L2POLICY");
-      q.l2_policy = e ? std::atoi(e) : 1;
-    }
-    p->sweep_smem = f.smem_total;
-    p->sweep_key = key;
-  }
-  if (prof) prof->tick(0, st);   // the whole network is one launch: it IS the dominant kernel
-  SwParams prm = p->sweep_prm;
+  const int n = c.n_layers;
+  // (no device-side tables: every per-layer quantity is derived from these parameters inside the kernel, so a change
+  // of batch size, shape or workspace costs nothing)
+  SwParams prm{};
+  prm.wpack0 = reinterpret_cast<const unsigned char*>(p->wpack_sw[0]);
+  prm.kconst0 = reinterpret_cast<const unsigned char*>(p->shift_p[0]);
+  prm.layer_stride = n > 1 ? (int64_t)(reinterpret_cast<const unsigned char*>(p->wpack_sw[1]) - prm.wpack0) : 0;
+  prm.use_dilation = c.use_dilation ? 1 : 0;
+  prm.conv0_wb = reinterpret_cast<const unsigned char*>(f.split ? p->conv0_wb3 : p->conv0_wb);
+  prm.last_scale = p->scale_p[n - 1];
+  prm.out_w = p->out_w;
+  prm.out_b = p->out_b;
+  prm.P = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws));
+  prm.Q = reinterpret_cast<__nv_bfloat16*>(static_cast<char*>(ws) + buf);
+  prm.n_layers = n; prm.C = c.n_maps; prm.n_labels = c.n_labels; prm.T = T; prm.F = F;
+  prm.H = H; prm.W = W; prm.n_strips = f.n_strips;
+  prm.smem_c0w_off = f.c0w_off;
+  prm.smem_skip_off = f.skip_off;
+  prm.dmax = f.dmax;
+  prm.chunk_rows = f.chunk_rows;
+  prm.ring_slack_bytes = f.slack_bytes;
+  prm.k32 = f.k32 ? 1 : 0;
+  prm.discard_q = p->sweep_discard && f.n_strips == 1 && !f.split;
+  prm.smem_w_off[0] = f.w_off[0]; prm.smem_w_off[1] = f.w_off[1];
+  prm.smem_ring_off = f.ring_off; prm.ring_slot_bytes = f.slot_bytes; prm.n_stages = f.n_stages;
+  prm.l2_policy = p->l2_policy;
+  prm.wait_polls = p->wait_polls;
   prm.feat = feat;
   prm.logits = logits;
   prm.B = B;
+  if (prof) prof->tick(0, st);   // the whole network is one launch: it IS the dominant kernel
   const int grid = (int)std::min<int64_t>(f.n_slots, B);
   static const bool dbg_on = [] { const char* e = std::getenv("HONK2_TC_DEBUG"); return e && std::atoi(e) != 0; }();
   static long long* dbg_buf = nullptr;
-  if (dbg_on) {
+  if (dbg_on && !f.split) {
     if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
     prm.debug = dbg_buf;
-  }
-  if (dbg_on) { const char* e = std::getenv("HONK2_TC_DIAG"); prm.diag = e ? std::atoi(e) : 0; }
-  {
-    static const int polls = [] { const char* e = std::getenv("HONK2_TC_WAIT_POLLS"); return e ? std::atoi(e) : 48; }();
-    static bool polls_set = false;
-    if (!polls_set) { cudaMemcpyToSymbol(g_wait_polls, &polls, sizeof(int)); polls_set = true; }
+    const char* e = std::getenv("HONK2_TC_DIAG");
+    prm.diag = e ? std::atoi(e) : 0;
   }
   static const bool trace_on = [] { const char* e = std::getenv("HONK2_TC_TRACE"); return e && std::atoi(e) != 0; }();
   static long long* trace_buf = nullptr;
-  if (dbg_on && trace_on) {
+  if (prm.debug != nullptr && trace_on) {
     if (!trace_buf) { cudaMalloc(&trace_buf, 8 * kSwTraceLen * sizeof(long long)); }
     cudaMemsetAsync(trace_buf, 0, 8 * kSwTraceLen * sizeof(long long), st);
     prm.trace = trace_buf;
@@ -1586,38 +1546,41 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
               "previous column %.1f%%, math + stores (+ guard, tail) %.1f%%, conv_0 %.1f%% (total %.0f)\n",
               100 * h[8] / et, 100 * h[9] / et, 100 * h[10] / et, 100 * h[11] / et, 100 * h[12] / et, et);
     }
-  } dbg_print{dbg_on ? dbg_buf : nullptr, st, prm.trace};
+  } dbg_print{prm.debug, st, prm.trace};
   switch (p->NKC) {
-    case 1: return tc_launch_sweep<1>(prm, grid, p->sweep_smem, st);
-    case 2: return tc_launch_sweep<2>(prm, grid, p->sweep_smem, st);
-    case 3: return tc_launch_sweep<3>(prm, grid, p->sweep_smem, st);
-    default: return tc_launch_sweep<4>(prm, grid, p->sweep_smem, st);
+    case 1: return tc_launch_sweep<1>(prm, f.split, grid, f.smem_total, st);
+    case 2: return tc_launch_sweep<2>(prm, f.split, grid, f.smem_total, st);
+    default: return tc_launch_sweep<3>(prm, f.split, grid, f.smem_total, st);
   }
 }
 
-size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int chunk) {
+size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int chunk, bool split) {
   if (!p || !p->supported) return 0;
   int H, W;
   tc_map_hw(p->cfg, T, F, &H, &W);
   if (H < 1 || W < 1 || W > 256 || !tc_layers_ok(p, H, W)) return 0;
+  const TcSweepPlan sp = tc_sweep_plan(p, H, W, split);
+  const TcFusedPlan f = tc_fused_plan(p, H, W, split);
+  if (split) {   // the split-bf16 mode exists in the two whole-network kernels only
+    if (sp.ok) return tc_sweep_ws_bytes(p, sp, H, W, nullptr);
+    return f.ok ? tc_fused_ws_bytes(p, f, W, nullptr) : 0;
+  }
   const int64_t c = tc_chunk(p, B, H, W, chunk);
   const size_t layered = p->lanes * tc_lane_bytes(p, c, H, W, nullptr);
-  const TcFusedPlan f = tc_fused_plan(p, H, W);
   // the layer-per-launch path stays available (profiling, shapes the fused kernel cannot stage)
   size_t need = f.ok ? std::max(layered, tc_fused_ws_bytes(p, f, W, nullptr)) : layered;
-  const TcSweepPlan sp = tc_sweep_plan(p, H, W);
   if (sp.ok) need = std::max(need, tc_sweep_ws_bytes(p, sp, H, W, nullptr));
   return need;
 }
 
-const char* tc_resnet_kernel_path(const TcResNet* p, int T, int F) {
+const char* tc_resnet_kernel_path(const TcResNet* p, int T, int F, bool split) {
   if (!p || !p->supported) return "unsupported";
   int H, W;
   tc_map_hw(p->cfg, T, F, &H, &W);
   if (H < 1 || W < 1 || W > 256 || !tc_layers_ok(p, H, W)) return "unsupported";
-  if (tc_sweep_plan(p, H, W).ok) return "resnet_tc_sweep_kernel";
-  if (tc_fused_plan(p, H, W).ok) return "resnet_tc_fused_kernel";
-  return "conv3x3_tc_kernel";
+  if (tc_sweep_plan(p, H, W, split).ok) return "resnet_tc_sweep_kernel";
+  if (tc_fused_plan(p, H, W, split).ok) return "resnet_tc_fused_kernel";
+  return split ? "unsupported" : "conv3x3_tc_kernel";
 }
 
 template <int NKC, bool HAS_PREV, bool DO_POOL>
@@ -1650,7 +1613,7 @@ static int tc_launch_conv(const CUtensorMap& map, const TcConvParams& prm, int g
 }
 
 int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, float* logits, void* ws,
-                      size_t ws_bytes, int chunk_cfg, LaunchProfiler* prof, cudaStream_t st) {
+                      size_t ws_bytes, int chunk_cfg, bool split, LaunchProfiler* prof, cudaStream_t st) {
   if (!p->supported) {
     set_error("bf16 tensor-core path supports 1..64 feature maps (got %d) and needs cuTensorMapEncodeTiled",
               p->cfg.n_maps);
@@ -1660,9 +1623,9 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
   int H, W;
   tc_map_hw(c, T, F, &H, &W);
   KWS_REQUIRE(H >= 1 && W >= 1, "ResNet: input %dx%d is smaller than the pooling window", T, F);
-  const size_t need = tc_resnet_workspace_bytes(p, B, T, F, chunk_cfg);
+  const size_t need = tc_resnet_workspace_bytes(p, B, T, F, chunk_cfg, split);
   if (need == 0) {
-    set_error("bf16 tensor-core path cannot tile a %dx%d map", H, W);
+    set_error("%s tensor-core path cannot tile a %dx%d map", split ? "split-bf16" : "bf16", H, W);
     return KWS_ERR_UNSUPPORTED;
   }
   if (ws == nullptr || ws_bytes < need) {
@@ -1672,13 +1635,18 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
   {
     // whole-network persistent kernel unless per-launch profiling was requested
     static const bool prof_layered = [] { const char* e = std::getenv("HONK2_TC_PROFILE_LAYERED"); return e && std::atoi(e) != 0; }();
-    const TcSweepPlan sp = tc_sweep_plan(p, H, W);
-    if (sp.ok && !(prof && prof->enabled && prof_layered)) {
+    const bool layered = prof && prof->enabled && prof_layered && !split;
+    const TcSweepPlan sp = tc_sweep_plan(p, H, W, split);
+    if (sp.ok && !layered) {
       return tc_sweep_forward(p, sp, feat, B, T, F, H, W, logits, ws, prof, st);
     }
-    const TcFusedPlan f = tc_fused_plan(p, H, W);
-    if (f.ok && !(prof && prof->enabled && prof_layered)) {
+    const TcFusedPlan f = tc_fused_plan(p, H, W, split);
+    if (f.ok && !layered) {
       return tc_fused_forward(p, f, feat, B, T, F, H, W, logits, ws, prof, st);
+    }
+    if (split) {
+      set_error("split-bf16 tensor-core path: no whole-network kernel can stage a %dx%d map", H, W);
+      return KWS_ERR_UNSUPPORTED;
     }
   }
   const int64_t chunk = tc_chunk(p, B, H, W, chunk_cfg);

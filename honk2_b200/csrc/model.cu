@@ -20,7 +20,7 @@ struct Model {
   kws_cnn_config cc{};
   bool weights_set = false;
   int64_t last_launches = 0;
-  int chunk[2] = {0, 0};
+  int chunk[3] = {0, 0, 0};   // per precision
   LaunchProfiler prof;
 
   // ---- ResNet fp32 packed weights
@@ -466,7 +466,8 @@ extern "C" size_t kws_model_workspace_bytes(const kws_model_t* m, int64_t B, int
   if (B == 0) return 256;
   if (m->kind == KIND_RESNET) {
     if (precision == KWS_FP32) return resnet_ws_f32(m, B, T, F, nullptr);
-    if (precision == KWS_BF16) return tc_resnet_workspace_bytes(m->tc, B, T, F, m->chunk[KWS_BF16]);
+    if (precision == KWS_BF16 || precision == KWS_BF16X3)
+      return tc_resnet_workspace_bytes(m->tc, B, T, F, m->chunk[precision], precision == KWS_BF16X3);
     return 0;
   }
   if (precision == KWS_FP32) return cnn_ws_f32(m, B, nullptr);
@@ -478,7 +479,8 @@ extern "C" int kws_model_forward(kws_model_t* m, const float* feat, int64_t B, i
   KWS_REQUIRE(m != nullptr, "kws_model_forward: model is null");
   KWS_REQUIRE(m->weights_set, "kws_model_forward: weights were never set");
   KWS_REQUIRE(B >= 0 && T >= 1 && F >= 1, "kws_model_forward: bad shape B=%lld T=%d F=%d", (long long)B, T, F);
-  KWS_REQUIRE(precision == KWS_FP32 || precision == KWS_BF16, "kws_model_forward: unknown precision %d", precision);
+  KWS_REQUIRE(precision == KWS_FP32 || precision == KWS_BF16 || precision == KWS_BF16X3,
+              "kws_model_forward: unknown precision %d", precision);
   if (B == 0) return KWS_OK;
   KWS_REQUIRE(feat != nullptr && logits != nullptr, "kws_model_forward: null buffer");
   g_launches = 0;
@@ -487,11 +489,11 @@ extern "C" int kws_model_forward(kws_model_t* m, const float* feat, int64_t B, i
     if (precision == KWS_FP32)
       st = resnet_forward_f32(m, feat, B, T, F, logits, workspace, workspace_bytes, as_stream(stream));
     else
-      st = tc_resnet_forward(m->tc, feat, B, T, F, logits, workspace, workspace_bytes, m->chunk[KWS_BF16],
-                             &m->prof, as_stream(stream));
+      st = tc_resnet_forward(m->tc, feat, B, T, F, logits, workspace, workspace_bytes, m->chunk[precision],
+                             precision == KWS_BF16X3, &m->prof, as_stream(stream));
   } else {
     if (precision != KWS_FP32) {
-      set_error("kws_model_forward: the CNN family has no bf16 tensor-core path yet");
+      set_error("kws_model_forward: the CNN family has no tensor-core path yet");
       return KWS_ERR_UNSUPPORTED;
     }
     st = cnn_forward_f32(m, feat, B, T, F, logits, workspace, workspace_bytes, as_stream(stream));
@@ -525,14 +527,14 @@ extern "C" int kws_model_forward_wave(kws_model_t* m, const kws_frontend_t* fe, 
     set_error("kws_model_forward_wave needs %zu bytes of workspace, got %zu", need, workspace_bytes);
     return KWS_ERR_WORKSPACE;
   }
+  // the model's scratch comes FIRST: its address (which the whole-network kernels' cached tensor maps are keyed on)
+  // then does not move when the batch size, and with it the size of the feature buffer, changes
   const size_t feat_bytes = round_up<size_t>((size_t)B * T * F * sizeof(float), 256);
-  float* feat = reinterpret_cast<float*>(workspace);
+  const size_t model_bytes = need - feat_bytes;
+  float* feat = reinterpret_cast<float*>(static_cast<char*>(workspace) + model_bytes);
   KWS_TRY(kws_mfcc_forward(fe, wav, B, n_samples, feat, stream));
-  const int64_t fe_launches = g_launches;
-  int st = kws_model_forward(m, feat, B, T, F, logits, precision, static_cast<char*>(workspace) + feat_bytes,
-                             workspace_bytes - feat_bytes, stream);
+  int st = kws_model_forward(m, feat, B, T, F, logits, precision, workspace, model_bytes, stream);
   m->last_launches += 1;
-  (void)fe_launches;
   return st;
 }
 
@@ -540,8 +542,8 @@ extern "C" int64_t kws_model_last_launches(const kws_model_t* m) { return m ? m-
 
 extern "C" const char* kws_model_kernel_path(const kws_model_t* m, int T, int F, int precision) {
   if (m == nullptr) return "unsupported";
-  if (precision != KWS_BF16) return "fp32 CUDA-core kernels";
-  return m->tc != nullptr ? tc_resnet_kernel_path(m->tc, T, F) : "unsupported";
+  if (precision != KWS_BF16 && precision != KWS_BF16X3) return "fp32 CUDA-core kernels";
+  return m->tc != nullptr ? tc_resnet_kernel_path(m->tc, T, F, precision == KWS_BF16X3) : "unsupported";
 }
 
 extern "C" int kws_model_set_profile(kws_model_t* m, int enabled) {
@@ -564,7 +566,8 @@ extern "C" int kws_model_profile_read(kws_model_t* m, double* conv_ms, int64_t* 
 
 extern "C" int kws_model_set_chunk(kws_model_t* m, int precision, int chunk) {
   KWS_REQUIRE(m != nullptr, "kws_model_set_chunk: model is null");
-  KWS_REQUIRE(precision == KWS_FP32 || precision == KWS_BF16, "kws_model_set_chunk: unknown precision");
+  KWS_REQUIRE(precision == KWS_FP32 || precision == KWS_BF16 || precision == KWS_BF16X3,
+              "kws_model_set_chunk: unknown precision");
   KWS_REQUIRE(chunk >= 0 && chunk <= 65535, "kws_model_set_chunk: chunk must be in [0, 65535]");
   m->chunk[precision] = chunk;
   return KWS_OK;

@@ -16,6 +16,11 @@
 // layers the CTA drains: epilogue stores -> __threadfence + fence.proxy.async -> __syncthreads ->
 // the producer may issue TMA loads of what was just written.  Weights of layer i+1 are bulk-copied
 // into the second weight buffer while layer i runs.
+//
+// SPLIT (the "bf16x3" precision): activations and weights are carried as bf16 pairs hi + lo (planes 0 .. NP-1 hold the
+// hi parts, NP .. 2 NP-1 the lo parts; the lo weight set follows the hi set) and every product is three MMAs,
+// hi*hi + hi*lo + lo*hi, accumulated in fp32: fp32-grade logits at a third of the bf16 MMA rate.  The two weight sets
+// of a layer share ONE buffer, loaded at the start of the layer (the CTA has just drained anyway).
 #pragma once
 
 namespace kws {
@@ -42,7 +47,7 @@ struct TcFusedParams {
   const float* out_w;            // [n_labels][C]
   const float* out_b;            // [n_labels]
   float* logits;                 // [B][n_labels]
-  __nv_bfloat16* P;              // [n_slots][NP][Hpad][W][8]
+  __nv_bfloat16* P;              // [n_slots][NP][Hpad][W][8]  (SPLIT: 2 NP planes per slot)
   __nv_bfloat16* Q;
   int64_t B;
   int n_layers, C, n_labels, T, F, ph, pw, H, W, Hpad;
@@ -51,15 +56,18 @@ struct TcFusedParams {
   int l2_policy;   // 1: buffer P (read twice, rewritten in place) evict_last, buffer Q (write once, read once) evict_first
 };
 
-template <int NKC>
+template <int NKC, bool SPLIT>
 __global__ void __launch_bounds__(tc_threads(NKC), 1)
 resnet_tc_fused_kernel(const TcFusedParams p) {
   constexpr int kThreads = tc_threads(NKC);
   constexpr int kEpiWarps = tc_epi_warps(NKC);
   constexpr int CP = 16 * NKC;
   constexpr int NP = 2 * NKC;
+  constexpr int NPX = SPLIT ? 2 * NP : NP;             // planes per utterance slot
+  constexpr int NA = SPLIT ? 2 * NKC : NKC;            // staged 16-channel chunks per tile (SPLIT: hi chunks, then lo chunks)
   constexpr int W_HALF = CP * 16;
-  constexpr int W_BYTES = 9 * NKC * 2 * W_HALF;
+  constexpr int W_PART = 9 * NKC * 2 * W_HALF;         // one weight set
+  constexpr int W_BYTES = (SPLIT ? 2 : 1) * W_PART;
   constexpr int MAXMT = (kAccCols / CP) < kTcMaxMt ? (kAccCols / CP) : kTcMaxMt;
   constexpr int MAXU = (MAXMT + kTcIssuers - 1) / kTcIssuers;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -92,9 +100,11 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
     mbar_init(wfull_bar(0), 1);
     mbar_init(wfull_bar(1), 1);
     fence_barrier_init();
-    if (n_seq > 0) {   // weights + descriptor of the first layer
-      mbar_expect_tx(wfull_bar(0), W_BYTES);
-      bulk_load(smem_u32(smem + p.smem_w_off[0]), p.layers[0].wpack, W_BYTES, wfull_bar(0));
+    if (n_seq > 0) {   // weights + descriptor of the first layer (SPLIT loads every layer's weights at its start)
+      if constexpr (!SPLIT) {
+        mbar_expect_tx(wfull_bar(0), W_BYTES);
+        bulk_load(smem_u32(smem + p.smem_w_off[0]), p.layers[0].wpack, W_BYTES, wfull_bar(0));
+      }
       s_layer[0] = p.layers[0];
     }
   }
@@ -113,7 +123,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   const int64_t plane_stride = (int64_t)p.Hpad * p.W;                    // 16-byte units
-  const int64_t slot_base = (int64_t)blockIdx.x * NP * plane_stride;     // this CTA's utterance slot
+  const int64_t slot_base = (int64_t)blockIdx.x * NPX * plane_stride;    // this CTA's utterance slot
   uint4* bufP = reinterpret_cast<uint4*>(p.P) + slot_base;
   uint4* bufQ = reinterpret_cast<uint4*>(p.Q) + slot_base;
 
@@ -189,6 +199,16 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
                 for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(a4[px][2 * e], a4[px][2 * e + 1]);
                 uint4* dst = bufP + pl * plane_stride + (int64_t)h * p.W + w0 + px;
                 if (use_pol) st_hint(dst, o, pol_keep); else *dst = o;
+                if constexpr (SPLIT) {   // lo part: x - float(hi)
+                  uint4 o2;
+                  __nv_bfloat162* ob2 = reinterpret_cast<__nv_bfloat162*>(&o2);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 fh = __bfloat1622float2(ob[e]);
+                    ob2[e] = __floats2bfloat162_rn(a4[px][2 * e] - fh.x, a4[px][2 * e + 1] - fh.y);
+                  }
+                  if (use_pol) st_hint(dst + NP * plane_stride, o2, pol_keep); else dst[NP * plane_stride] = o2;
+                }
               }
             }
           }
@@ -229,6 +249,16 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(a8[2 * e] * inv, a8[2 * e + 1] * inv);
           bufP[pl * plane_stride + pix] = o;
+          if constexpr (SPLIT) {
+            uint4 o2;
+            __nv_bfloat162* ob2 = reinterpret_cast<__nv_bfloat162*>(&o2);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fh = __bfloat1622float2(ob[e]);
+              ob2[e] = __floats2bfloat162_rn(a8[2 * e] * inv - fh.x, a8[2 * e + 1] * inv - fh.y);
+            }
+            bufP[(NP + pl) * plane_stride + pix] = o2;
+          }
         }
       }
       }
@@ -249,12 +279,22 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
         // ================================ TMA producer ================================
         // prefetch the next step's weights / descriptor / constants into the other buffers
         // (free: the layer that used them finished before the barrier we just passed)
+        if constexpr (SPLIT) {
+          // one weight buffer: this layer's two weight sets now (every MMA of the previous layer has retired: its
+          // epilogue read all accumulators before the barrier we just passed)
+          if (lane == 0) {
+            mbar_expect_tx(wfull_bar(cur), W_BYTES);
+            bulk_load(w_smem, L.wpack, W_BYTES, wfull_bar(cur));
+          }
+        }
         if (seq + 1 < n_seq) {
           const int nl = (l + 1 < n_layers) ? l + 1 : 0;
           const TcLayerDesc* nd = p.layers + nl;
           if (lane == 0) {
-            mbar_expect_tx(wfull_bar(cur ^ 1), W_BYTES);
-            bulk_load(smem_u32(smem + p.smem_w_off[cur ^ 1]), nd->wpack, W_BYTES, wfull_bar(cur ^ 1));
+            if constexpr (!SPLIT) {
+              mbar_expect_tx(wfull_bar(cur ^ 1), W_BYTES);
+              bulk_load(smem_u32(smem + p.smem_w_off[cur ^ 1]), nd->wpack, W_BYTES, wfull_bar(cur ^ 1));
+            }
             s_layer[cur ^ 1] = *nd;
           }
           for (int i = lane; i < CP; i += 32) s_kconst[(cur ^ 1) * CP + i] = nd->kconst[i];
@@ -266,7 +306,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
             int ph, r0, rows;
             tile_decode(g, tix, ph, r0, rows);
             if (rows <= 0) continue;
-            for (int kc = 0; kc < NKC; ++kc) {
+            for (int kc = 0; kc < NA; ++kc) {
               mbar_wait(empty_bar(stage), phase ^ 1);
               mbar_expect_tx(full_bar(stage), tx);
               const uint32_t sbase = smem_u32(s_ring + (size_t)stage * p.ring_slot_bytes);
@@ -274,11 +314,11 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
                 for (int bx = 0; bx < g.n_boxes; ++bx)
                   if (use_pol)
                     tma_load_5d_hint(sbase + half * g.slab_bytes + bx * g.box_stride, map, full_bar(stage), 0, -g.dpad,
-                                     r0 + g.h_start[bx], ph, (int)blockIdx.x * NP + 2 * kc + half,
+                                     r0 + g.h_start[bx], ph, (int)blockIdx.x * NPX + 2 * kc + half,
                                      L.in_buf ? pol_stream : pol_keep);
                   else
                     tma_load_5d(sbase + half * g.slab_bytes + bx * g.box_stride, map, full_bar(stage), 0, -g.dpad,
-                                r0 + g.h_start[bx], ph, (int)blockIdx.x * NP + 2 * kc + half);
+                                r0 + g.h_start[bx], ph, (int)blockIdx.x * NPX + 2 * kc + half);
               if (++stage == kFusedStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -310,7 +350,8 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
           if (dbg) { const long long t = clock64(); dbg_tempty += t - dbg_t; dbg_t = t; }
           const uint32_t d_base = tmem_base + acc * kAccCols + me * CP;
 #pragma unroll
-          for (int kc = 0; kc < NKC; ++kc) {
+          for (int kca = 0; kca < NA; ++kca) {
+            const int kc = kca < NKC ? kca : kca - NKC;   // weight chunk (SPLIT: stages NKC .. 2 NKC-1 hold the lo parts)
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             if (dbg) { const long long t = clock64(); dbg_full += t - dbg_t; dbg_t = t; }
@@ -322,7 +363,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
                 if ((tap % 3) != 1 && !side) continue;
                 const uint32_t a_lo = a_lo_stage + (uint32_t)tap16[tap];
                 const uint32_t b_lo = b_lo_base + (uint32_t)(((tap * NKC + kc) * 2 * W_HALF) >> 4);
-                if (kc == 0 && tap <= 1) {
+                if (kca == 0 && tap <= 1) {
                   const uint32_t accum = (tap == first_tap) ? 0u : 1u;
 #pragma unroll
                   for (int u = 0; u < MAXU; ++u)
@@ -334,9 +375,18 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
                     if (me + u * kTcIssuers < n_mt)
                       umma_f16_lohi<true>(d_base + u * kTcIssuers * CP, a_lo + u * kTcIssuers * 128, b_lo, desc_hi, idesc);
                 }
+                if constexpr (SPLIT) {
+                  if (kca < NKC) {   // hi activations x lo weights (the lo set follows the hi set; no carry: < 256 KB)
+#pragma unroll
+                    for (int u = 0; u < MAXU; ++u)
+                      if (me + u * kTcIssuers < n_mt)
+                        umma_f16_lohi<true>(d_base + u * kTcIssuers * CP, a_lo + u * kTcIssuers * 128,
+                                            b_lo + (uint32_t)(W_PART >> 4), desc_hi, idesc);
+                  }
+                }
               }
               umma_commit(empty_bar(stage));
-              if (kc == NKC - 1) umma_commit(tfull_bar(acc));
+              if (kca == NA - 1) umma_commit(tfull_bar(acc));
             }
             __syncwarp();
             if (dbg) { const long long t = clock64(); dbg_issue += t - dbg_t; dbg_t = t; }
@@ -373,29 +423,33 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
             valid = (w >= 0) && (r < rows) && (mt < n_mt);
             return tile_base + (int64_t)(r * hstep) * g.W + w;
           };
-          uint4 pv_next[2];
+          constexpr int NSK = SPLIT ? 4 : 2;   // skip registers: planes 2j, 2j+1 (SPLIT: and their lo planes)
+          auto load_skip = [&](int64_t b0, uint4 (&dst)[NSK]) {
+            dst[0] = use_pol ? ld_hint(skip_in + b0, pol_keep) : skip_in[b0];
+            dst[1] = use_pol ? ld_hint(skip_in + b0 + plane_stride, pol_keep) : skip_in[b0 + plane_stride];
+            if constexpr (SPLIT) {
+              dst[2] = use_pol ? ld_hint(skip_in + b0 + NP * plane_stride, pol_keep) : skip_in[b0 + NP * plane_stride];
+              dst[3] = use_pol ? ld_hint(skip_in + b0 + (NP + 1) * plane_stride, pol_keep) : skip_in[b0 + (NP + 1) * plane_stride];
+            }
+          };
+          uint4 pv_next[NSK];
           if (has_skip) {
             bool v0;
             const int64_t b0 = locate(0, v0);
-            if (v0) {
-              pv_next[0] = use_pol ? ld_hint(skip_in + b0, pol_keep) : skip_in[b0];
-              pv_next[1] = use_pol ? ld_hint(skip_in + b0 + plane_stride, pol_keep) : skip_in[b0 + plane_stride];
-            }
+            if (v0) load_skip(b0, pv_next);
           }
           mbar_wait(tfull_bar(acc), acc_phase);
           tc_fence_after();
           for (int mt = 0; mt < n_mt; ++mt) {
             bool valid;
             const int64_t base = locate(mt, valid);
-            uint4 pv[2];
+            uint4 pv[NSK];
             if (has_skip) {
-              pv[0] = pv_next[0]; pv[1] = pv_next[1];
+#pragma unroll
+              for (int k = 0; k < NSK; ++k) pv[k] = pv_next[k];
               bool v2;
               const int64_t b2 = locate(mt + 1, v2);
-              if (v2) {
-                pv_next[0] = use_pol ? ld_hint(skip_in + b2, pol_keep) : skip_in[b2];
-                pv_next[1] = use_pol ? ld_hint(skip_in + b2 + plane_stride, pol_keep) : skip_in[b2 + plane_stride];
-              }
+              if (v2) load_skip(b2, pv_next);
             }
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols + mt * CP + 16 * j, v);
@@ -414,6 +468,15 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
                     x[2 * e] += f.x;
                     x[2 * e + 1] += f.y;
                   }
+                  if constexpr (SPLIT) {
+                    const __nv_bfloat162* pl2 = reinterpret_cast<const __nv_bfloat162*>(&pv[2 + hf]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f = __bfloat1622float2(pl2[e]);
+                      x[2 * e] += f.x;
+                      x[2 * e + 1] += f.y;
+                    }
+                  }
                 }
                 if (last) {
 #pragma unroll
@@ -425,6 +488,17 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
                   for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
                   if (use_pol) st_hint(y_out + base + hf * plane_stride, yo, has_skip ? pol_keep : pol_stream);
                   else y_out[base + hf * plane_stride] = yo;
+                  if constexpr (SPLIT) {   // lo part: x - float(hi)
+                    uint4 yl;
+                    __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&yl);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 fh = __bfloat1622float2(yb[e]);
+                      lb[e] = __floats2bfloat162_rn(x[2 * e] - fh.x, x[2 * e + 1] - fh.y);
+                    }
+                    if (use_pol) st_hint(y_out + base + (NP + hf) * plane_stride, yl, has_skip ? pol_keep : pol_stream);
+                    else y_out[base + (NP + hf) * plane_stride] = yl;
+                  }
                 }
               }
             }

@@ -17,12 +17,20 @@
 // Every MMA accumulates: the epilogue zeroes a ring block right after reading it.  A window that wraps around the
 // ring is issued as two narrower MMAs (N = 96 + 48).
 //
-// Activation layout ("column planar-8"): [slot][NP][W][H][8] bf16, one slot (buffers P and Q) per CTA.  A staged
-// column is [NP planes][rows -d .. 128+d][8 ch] in shared memory = the K-major SWIZZLE_NONE canonical layout (row
-// pitch 16 B, plane pitch = LBO); rows outside the map are zero, which is exactly the reference's zero padding
-// (resnet.py:22-24, padding = dilation), and the +-d row shift of a height tap is a descriptor start-address
-// offset.  Single-strip maps (H <= 128) are staged with one cp.async.bulk of H*16 contiguous bytes per plane into a
-// slot whose pad rows were zeroed once; taller maps with 4-D TMA boxes (out-of-bounds zero fill).
+// Activation layouts, one slot (buffers P and Q) per CTA, staged by 1-D bulk copies (cp.async.bulk):
+//   single-strip maps (H <= 128): [slot][K chunk][W][H][16 ch = 32 B] bf16; a staged column is [chunk][pad | H rows |
+//     pad][32 B] in shared memory, read as a SWIZZLE_32B K-major operand, one copy of H*32 contiguous bytes per chunk
+//     into a slot whose pad rows were zeroed once;
+//   taller maps ("column planar-8"): [slot][NP][W][H][8] bf16; a staged column is [NP planes][rows -d .. 128+d][8 ch]
+//     = the K-major SWIZZLE_NONE canonical layout (row pitch 16 B, plane pitch = LBO), one copy per plane of the rows
+//     of the strip's window that lie inside the map.
+// Rows outside the map are zero, which is exactly the reference's zero padding (resnet.py:22-24, padding =
+// dilation), and the +-d row shift of a height tap is a descriptor start-address offset.
+//
+// SPLIT (the "bf16x3" precision, single-strip maps): every activation and weight is carried as a bf16 pair hi + lo
+// (hi = bf16(v), lo = bf16(v - hi): 16 mantissa bits) -- chunks 0 .. NKC-1 hold the hi parts, NKC .. 2 NKC-1 the lo
+// parts -- and each product is three MMAs, hi*hi + lo*hi + hi*lo, accumulated in fp32 in TMEM: the logits agree with
+// the fp32 reference arithmetic to ~1e-5 instead of ~3e-3, at a third of the bf16 MMA rate.
 //
 // conv_0 (1 -> C, resnet.py:18) runs in the same pipeline as a pseudo-layer with ONE 16-channel chunk whose only
 // live "channels" are the bf16 high and low parts of the fp32 feature (the weight slab holds w in both positions, so
@@ -78,12 +86,14 @@ struct SwParams {
   // (resnet.py:21), reads Q and adds the skip tensor iff l is odd (resnet.py:51-53), and its packed weights /
   // epilogue constants sit at a fixed stride.
   const unsigned char* wpack0;  // layer 0 weights, [NKC][3 dh][2 K halves][3 blocks][CP][8] bf16; block k = width tap dw = 2 - k
+                                //   (SPLIT: the hi parts in that layout, followed by the lo parts in the same layout)
   const unsigned char* kconst0; // layer 0 epilogue constants, [CP] f32 (see pad_bn_kernel)
   int64_t layer_stride;         // bytes between consecutive layers in both arrays
-  const CUtensorMap* maps;      // [n_layers]  input tensor map of every layer (global memory, 64 B aligned)
   int use_dilation;
   const float* feat;            // [B][T][F]
   const unsigned char* conv0_wb; // conv_0 weights as a one-chunk sweep slab set: [3 dh][2 K halves][3 blocks][CP][8] bf16
+                                //   (k = 0, 1: bf16(w) against the feature's hi and lo parts; SPLIT: k = 2 holds w - bf16(w)
+                                //   against a second copy of the feature's hi part)
   const float* last_scale;      // [CP]
   const float* out_w;           // [n_labels][C]
   const float* out_b;           // [n_labels]
@@ -95,27 +105,30 @@ struct SwParams {
   int n_strips;                 // ceil(H / 128)
   int smem_c0w_off;             // conv_0 weight slabs (3 * 2 * 3*CP*16 bytes), resident for the whole kernel
   int smem_w_off[2], smem_ring_off, ring_slot_bytes, n_stages;
-  int smem_skip_off;            // skip staging: one slot of NP * 2048 bytes per epilogue warp group
+  int smem_skip_off;            // skip staging: one slot of NP * 2048 bytes per epilogue warp group (unused by SPLIT)
+  int ring_slack_bytes;         // zeroed bytes behind the last stage (see chunk_rows)
   int l2_policy;
-  int bulk_rows;                // != 0: columns are staged with one 1-D bulk copy per plane (the rows of the strip's window
-                                //   that lie inside the map) into a fixed [plane][128 + 2 dmax] slot; pad rows are zero
-                                //   (single strip: zeroed once and never written; several strips: re-zeroed by the producer
-                                //   for the strips that touch the map's top / bottom).  0: TMA tensor boxes
-  int dmax;                     // largest dilation of the network (bulk path: data row h sits at slot row dmax + h)
-  int packed;                   // 1 = P / Q hold whole COLUMNS contiguously, [w][pad dmax | plane 0 | pad | plane 1 | ... | pad] (single strip)
-  int col_rows;                 // planar layout: rows between consecutive columns of a plane (H, or H rounded up to 8 = whole 128-byte lines)
-  int k32;                      // 1 = activations as [K chunk][w][h][16 channels = 32 B] (single strip): NKC copies per step,
-                                //     swizzle-32B A operand; the two 16-byte halves of a row are stored swapped where
+  int chunk_rows;               // rows per plane / chunk of a staged column (a multiple of 8): data row h of the strip sits at
+                                //   slot row dmax + h, the pad rows above and below are zero (single strip: zeroed once and
+                                //   never written; several strips: re-zeroed by the producer for the strips that touch the
+                                //   map's top / bottom).  128 + 2 dmax, or H + 2 dmax rounded up when the map is shorter than
+                                //   a strip (the lanes past the map then read into the next chunk: their results are unused)
+  int dmax;                     // largest dilation of the network
+  int k32;                      // 1 = activations as [K chunk][w][h][16 channels = 32 B] (single strip): one copy per chunk and
+                                //     step, swizzle-32B A operand; the two 16-byte halves of a row are stored swapped where
                                 //     ((dmax + h) >> 2) & 1, i.e. exactly as the linear copy must land them in the slot
+  int wait_polls;               // barrier polls before a wait falls back to the suspending try_wait (HONK2_TC_WAIT_POLLS)
   int discard_q;                // 1 = Q columns are discarded from L2 (no write-back) once the layer that reads them has consumed them
   int diag;                     // diagnostics (wrong results!): 1 = epilogue skips math and stores, 2 = skips the skip-tensor loads
   long long* debug;             // optional cycle counters of CTA 0 (HONK2_TC_DEBUG=1)
   long long* trace;             // optional [8][kSwTraceLen] event timestamps of CTA 0 (HONK2_TC_TRACE=1, needs DEBUG)
 };
 
-template <int NKC, bool DBG, bool K32>
+template <int NKC, bool DBG, bool K32, bool SPLIT>
 __global__ void __launch_bounds__(sw_threads(NKC), 1)
 resnet_tc_sweep_kernel(const SwParams p) {
+  static_assert(K32 || !SPLIT, "the split-bf16 mode is built on the 32-byte-row layout");
+  constexpr int NA = SPLIT ? 2 * NKC : NKC;            // activation chunks staged per column (SPLIT: hi chunks, then lo chunks)
   constexpr int kEpiWarps = sw_epi_warps(NKC);
   constexpr int kEpiThreads = 32 * kEpiWarps;
   constexpr int CP = 16 * NKC;
@@ -124,7 +137,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
   constexpr int BLK_BYTES = CP * 16;                   // one [CP][8] weight block
   constexpr int W_LBO = 3 * BLK_BYTES;                 // distance between the two K halves of a weight slab
   constexpr int W_SLAB = 2 * W_LBO;                    // one (kc, dh) slab
-  constexpr int W_BYTES = NKC * 3 * W_SLAB;
+  constexpr int W_PART = NKC * 3 * W_SLAB;             // one set of slabs (SPLIT: the lo set follows the hi set)
+  constexpr int W_BYTES = (SPLIT ? 2 : 1) * W_PART;
   extern __shared__ __align__(1024) unsigned char smem[];
 
   const uint32_t sbase = smem_u32(smem);
@@ -150,18 +164,13 @@ resnet_tc_sweep_kernel(const SwParams p) {
   const int nl1 = n_layers + 1;                 // pseudo-layers per utterance: conv_0, then the C -> C layers
 
   // Activation layout in HBM (16-byte units = 8 bf16 channels of one position), one slot per CTA:
-  //   planar  [plane][w][h]                                   (multi-strip maps, TMA fallback)
-  //   packed  [w][ dmax zero rows | plane 0: H rows | dmax zero rows | plane 1 | ... | dmax zero rows ]
-  // The packed form makes a staged column ONE contiguous run: one bulk copy per step instead of NP, and the zero rows
-  // between planes (shared by the plane above and the plane below) are the convolution's height padding.
-  const bool packed = p.packed != 0;
+  //   k32     [K chunk][w][h][2]      (single-strip maps; SPLIT: 2 NKC chunks, the lo parts after the hi parts)
+  //   planar  [plane][w][h]           (multi-strip maps)
   constexpr bool k32 = K32;   // (compile time: the two layouts' address arithmetic would not fit the epilogue's registers together)
   const int64_t kc_stride = (int64_t)W * H * 2;   // k32: 16-byte units between K chunks
-  const int PP = H + p.dmax;                    // packed: plane pitch (rows)
-  const int COLP = NP * PP + p.dmax;            // packed: column pitch (rows)
-  const int col_pitch = packed ? COLP : p.col_rows, col_base = packed ? p.dmax : 0;
-  const int64_t plane_stride = packed ? (int64_t)PP : (int64_t)W * col_pitch;   // 16-byte units
-  const int64_t slot_base = (int64_t)blockIdx.x * (packed ? (int64_t)W * COLP : (int64_t)NP * W * col_pitch);   // this CTA's utterance slot
+  const int64_t plane_stride = (int64_t)W * H;    // planar: 16-byte units between planes
+  const int64_t slot_base = (int64_t)blockIdx.x * ((int64_t)(SPLIT ? 2 : 1) * NP * W * H);   // this CTA's utterance slot
+  auto wait_lean = [&](uint32_t bar, uint32_t parity) { mbar_wait_lean(bar, parity, p.wait_polls); };
   uint4* bufP = reinterpret_cast<uint4*>(p.P) + slot_base;
   uint4* bufQ = reinterpret_cast<uint4*>(p.Q) + slot_base;
 
@@ -192,24 +201,12 @@ resnet_tc_sweep_kernel(const SwParams p) {
       s_kc[i] = ll == 0 ? 0.f : reinterpret_cast<const float*>(p.kconst0 + (ll - 1) * p.layer_stride)[c];
     }
   }
-  if (p.bulk_rows > 0) {
-    // bulk-copy staging: the pad rows above and below the map are never written again and supply the zero padding
+  {
+    // the pad rows above and below the map are never written again and supply the zero padding (the slack behind the
+    // last stage is only ever read by lanes past the map)
     uint4* ring = reinterpret_cast<uint4*>(smem + p.smem_ring_off);
-    const int n16 = p.n_stages * (p.ring_slot_bytes >> 4);
+    const int n16 = (p.n_stages * p.ring_slot_bytes + p.ring_slack_bytes) >> 4;
     for (int i = threadIdx.x; i < n16; i += sw_threads(NKC)) ring[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  if (packed) {
-    // the zero rows of this CTA's slot (the workspace is scratch: nothing is assumed about its contents); the epilogue
-    // only ever stores data rows, so they stay zero for the whole launch
-    const int pad_rows = (NP + 1) * p.dmax;
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = threadIdx.x; i < W * pad_rows; i += sw_threads(NKC)) {
-      const int w = i / pad_rows, k = i - w * pad_rows, region = k / p.dmax, rr = k - region * p.dmax;
-      const int row = region == 0 ? rr : p.dmax + (region - 1) * PP + H + rr;
-      bufP[(int64_t)w * COLP + row] = z;
-      bufQ[(int64_t)w * COLP + row] = z;
-    }
-    fence_async_global();   // read by this CTA's bulk copies (async proxy)
   }
   fence_async_smem();   // generic-proxy writes (zeros, conv_0 weights) -> visible to the tensor core's (async proxy) reads
   tc_fence_before();
@@ -233,10 +230,10 @@ resnet_tc_sweep_kernel(const SwParams p) {
   const uint64_t pol_stream = p.l2_policy == 2 ? l2_policy_evict_normal() : l2_policy_evict_first();
 
   auto layer_dil = [&](int l) { return p.use_dilation ? (1 << (l / 3)) : 1; };
-  // rows per plane of a staged column = plane pitch in shared memory (kept a multiple of 8 rows = 128 B)
-  auto box_rows_of = [&](int d) { return packed ? PP : p.bulk_rows > 0 ? 128 + 2 * p.dmax : ((128 + 2 * d + 7) & ~7); };
+  // rows per plane / chunk of a staged column = its pitch in shared memory (a multiple of 8 rows)
+  const int box_rows = p.chunk_rows;
   // slot row that the height tap dh = 0 of output row 0 reads
-  auto row0_of = [&](int d) { return p.bulk_rows > 0 ? p.dmax - d : 0; };
+  auto row0_of = [&](int d) { return p.dmax - d; };
 
   if (warp == kEpiWarps) {
     // ========================================= TMA producer =========================================
@@ -264,17 +261,20 @@ resnet_tc_sweep_kernel(const SwParams p) {
         for (int ll = 0; ll < nl1; ++ll, ++sq) {
           const bool is_c0 = ll == 0;
           const int l = ll - 1;
-          const CUtensorMap* map = p.maps + (is_c0 ? 0 : l);
-          const int d = is_c0 ? 1 : layer_dil(l), box_rows = box_rows_of(d);
+          const int d = is_c0 ? 1 : layer_dil(l);
           const int n_runs = d < W ? d : W;
-          const uint32_t tx = (uint32_t)(NP * box_rows * 16);
           const bool in_q = !is_c0 && (l & 1) != 0;
           const uint64_t pol = in_q ? pol_stream : pol_keep;
           bool w_pending = !is_c0 && wq + 1 < n_wq;
           auto request_weights = [&]() {
-            // buffer (wq+1)&1 was read by the MMAs of the previous real layer: wait until they have retired
-            // (that layer is the previous pseudo-layer, or the one before conv_0 when this is the utterance's first)
-            if (wq >= 1) {
+            if constexpr (SPLIT) {
+              // ONE weight buffer (hi + lo slabs of a layer are 2 x 41 KB): the next layer's weights can only be
+              // requested when every MMA of THIS layer has retired -- a short bubble per layer, in a mode whose steps
+              // are three times as long
+              mbar_wait(layer_bar((int)(sq & 1)), (uint32_t)((sq >> 1) & 1));
+            } else if (wq >= 1) {
+              // buffer (wq+1)&1 was read by the MMAs of the previous real layer: wait until they have retired
+              // (that layer is the previous pseudo-layer, or the one before conv_0 when this is the utterance's first)
               const int64_t sp = l >= 1 ? sq - 1 : sq - 2;
               mbar_wait(layer_bar((int)(sp & 1)), (uint32_t)((sp >> 1) & 1));
             }
@@ -314,7 +314,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) { st[c] = t; ph[c] = q2; if (++t == p.n_stages) { t = 0; q2 ^= 1u; } } }
 #pragma unroll
-                  for (int c = 0; c < 4; ++c) if (c < cnt) mbar_wait_lean(empty_bar(st[c]), ph[c] ^ 1u);
+                  for (int c = 0; c < 4; ++c) if (c < cnt) wait_lean(empty_bar(st[c]), ph[c] ^ 1u);
                   pstamp(pd_empty);
                   float4 fr[5];
 #pragma unroll
@@ -331,7 +331,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
 #pragma unroll
                   for (int k = 0; k < 5; ++k) {
                     const int rr = lane + 32 * k;
-                    if (rr < 130) {
+                    if (rr < 130 && r0 + rr < box_rows) {   // (a chunk cut down to the map never needs the rows past it)
                       const float4 f = fr[k];
                       const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
@@ -339,14 +339,16 @@ resnet_tc_sweep_kernel(const SwParams p) {
                         if (c < cnt) {
                           const __nv_bfloat16 hi = __float2bfloat16_rn(fv[c]);
                           const __nv_bfloat16 lo = __float2bfloat16_rn(fv[c] - __bfloat162float(hi));
-                          const uint32_t packed = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+                          const uint32_t hilo = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+                          // SPLIT: channel 2 carries the hi part again, against the lo part of the weight
+                          const uint32_t hi2 = SPLIT ? (uint32_t)__bfloat16_as_ushort(hi) : 0u;
                           unsigned char* slot = smem + p.smem_ring_off + (size_t)st[c] * p.ring_slot_bytes;
                           if (k32) {   // 32-byte rows: channels 0-7 in the (swizzled) first half, zeros in the other
                             const int row = r0 + rr, sw = (row >> 2) & 1;
-                            *reinterpret_cast<uint4*>(slot + (size_t)row * 32 + (sw << 4)) = make_uint4(packed, 0u, 0u, 0u);
+                            *reinterpret_cast<uint4*>(slot + (size_t)row * 32 + (sw << 4)) = make_uint4(hilo, hi2, 0u, 0u);
                             *reinterpret_cast<uint4*>(slot + (size_t)row * 32 + ((sw ^ 1) << 4)) = make_uint4(0u, 0u, 0u, 0u);
                           } else
-                          *reinterpret_cast<uint4*>(slot + (size_t)(r0 + rr) * 16) = make_uint4(packed, 0u, 0u, 0u);
+                          *reinterpret_cast<uint4*>(slot + (size_t)(r0 + rr) * 16) = make_uint4(hilo, 0u, 0u, 0u);
                         }
                       }
                     }
@@ -373,31 +375,25 @@ resnet_tc_sweep_kernel(const SwParams p) {
           for (int s = 0; s < n_strips; ++s)
             for (int r = 0; r < n_runs; ++r)
               for (int w = r; w < W; w += d, ++step) {
-                if (w_pending && step == kSwWeightStep) request_weights();
+                if (!SPLIT && w_pending && step == kSwWeightStep) request_weights();
                 pstamp(pd_issue);
-                if (!is_c0) mbar_wait_lean(col_bar(prev_par, w), prev_phase);   // column w of the previous pseudo-layer is stored
+                if (!is_c0) wait_lean(col_bar(prev_par, w), prev_phase);   // column w of the previous pseudo-layer is stored
                 pstamp(pd_col);
-                mbar_wait_lean(empty_bar(stage), sphase ^ 1);
+                wait_lean(empty_bar(stage), sphase ^ 1);
                 pstamp(pd_empty);
                 const uint32_t dst = sbase + p.smem_ring_off + (uint32_t)stage * p.ring_slot_bytes;
                 if (k32) {
-                  // one contiguous H x 32 B run per 16-channel chunk
+                  // one contiguous H x 32 B run per 16-channel chunk (SPLIT: hi chunks, then lo chunks)
                   if (leader) {
                     const uint32_t bytes = (uint32_t)H * 32u;
-                    mbar_expect_tx(full_bar(stage), bytes * NKC);
+                    mbar_expect_tx(full_bar(stage), bytes * NA);
                     const uint4* src = (in_q ? bufQ : bufP) + (int64_t)w * H * 2;
                     const uint32_t d0 = dst + (uint32_t)p.dmax * 32u;
 #pragma unroll
-                    for (int kc = 0; kc < NKC; ++kc)
+                    for (int kc = 0; kc < NA; ++kc)
                       bulk_load_hint(d0 + (uint32_t)(kc * box_rows) * 32u, src + kc * kc_stride, bytes, full_bar(stage), pol);
                   }
-                } else if (packed) {
-                  // the whole column, zero rows included, in one copy
-                  if (leader) {
-                    mbar_expect_tx(full_bar(stage), (uint32_t)COLP * 16u);
-                    bulk_load_hint(dst, (in_q ? bufQ : bufP) + (int64_t)w * COLP, (uint32_t)COLP * 16u, full_bar(stage), pol);
-                  }
-                } else if (p.bulk_rows > 0) {
+                } else {
                   // one contiguous H x 16 B run per 8-channel plane (a TMA box with 16-byte rows fetches a whole
                   // 32-byte sector per row: 2.6x the bytes, measured with ncu)
                   // (issued by ONE lane with warp-uniform operands: per-lane operands would make the compiler wrap every
@@ -421,16 +417,12 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   const uint32_t bytes = (uint32_t)(h_hi - h_lo) * 16u;
                   if (leader) {
                     mbar_expect_tx(full_bar(stage), bytes * NP);
-                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)w * col_pitch + h_lo;
+                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)w * H + h_lo;
                     const uint32_t d0 = dst + (uint32_t)(p.dmax + h_lo - s * 128) * 16u;
 #pragma unroll
                     for (int pl = 0; pl < NP; ++pl)
                       bulk_load_hint(d0 + (uint32_t)(pl * box_rows) * 16u, src + (int64_t)pl * plane_stride, bytes, full_bar(stage), pol);
                   }
-                } else if (leader) {
-                  mbar_expect_tx(full_bar(stage), tx);
-                  if (use_pol) tma_load_4d_hint(dst, map, full_bar(stage), 0, s * 128 - d, w, (int)blockIdx.x * NP, pol);
-                  else tma_load_4d(dst, map, full_bar(stage), 0, s * 128 - d, w, (int)blockIdx.x * NP);
                 }
                 if constexpr (DBG) {
                   if (ptrace && leader && pstep < kSwTraceLen) p.trace[0 * kSwTraceLen + pstep] = clock64();
@@ -501,7 +493,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
         for (int ll = 0; ll < nl1; ++ll, ++sq) {
           const bool is_c0 = ll == 0;
           const int l = ll - 1;
-          const int d = is_c0 ? 1 : layer_dil(l), box_rows = box_rows_of(d);
+          const int d = is_c0 ? 1 : layer_dil(l);
           const int n_runs = d < W ? d : W;
           const int cur = (int)(sq & 1);
           const uint32_t plane16 = (uint32_t)box_rows;                       // plane pitch in 16-byte units
@@ -514,8 +506,11 @@ resnet_tc_sweep_kernel(const SwParams p) {
           const uint32_t kc_step = k32 ? (uint32_t)box_rows * 2u : 2u * plane16;     // 16-byte units per K chunk
           const uint32_t w16 = ((sbase + (is_c0 ? p.smem_c0w_off : p.smem_w_off[wq & 1])) >> 4);
           const uint32_t row0 = (uint32_t)row0_of(d);
+          // SPLIT: the lo chunks of the staged column follow the NKC hi chunks, the lo slabs follow the hi slabs
+          const uint32_t a_lo_off = (uint32_t)NKC * kc_step;
+          constexpr uint32_t b_lo_off = (uint32_t)(W_PART >> 4);
           stamp(dbg_other);
-          if (!is_c0) mbar_wait_lean(wfull_bar((int)(wq & 1)), (uint32_t)((wq >> 1) & 1));
+          if (!is_c0) wait_lean(wfull_bar((int)(wq & 1)), (uint32_t)((wq >> 1) & 1));
           stamp(dbg_w);
           for (int s = 0; s < n_strips; ++s)
             for (int r = 0; r < n_runs; ++r) {
@@ -533,12 +528,12 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   stamp(dbg_other);
                   tr(1);
                   // the epilogue must have drained and re-zeroed the previous use of every slot of the window
-                  if (lo) mbar_wait_lean(tempty_bar(s_lo), par_lo ^ 1u);
-                  mbar_wait_lean(tempty_bar(sl), pr ^ 1u);
-                  if (hi_) mbar_wait_lean(tempty_bar(s_hi), par_hi ^ 1u);
+                  if (lo) wait_lean(tempty_bar(s_lo), par_lo ^ 1u);
+                  wait_lean(tempty_bar(sl), pr ^ 1u);
+                  if (hi_) wait_lean(tempty_bar(s_hi), par_hi ^ 1u);
                   stamp(dbg_tempty);
                   tr(2);
-                  mbar_wait_lean(full_bar(stage), sphase);
+                  wait_lean(full_bar(stage), sphase);
                   tc_fence_after();
                   tr(3);
                   if constexpr (DBG) { if (is_c0 && s == 0 && r == 0 && i < kSwIssuers) stamp(dbg_utt); else stamp(dbg_full); }
@@ -560,7 +555,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   // together, then all three do their commits / bookkeeping / operand preparation at the same time and
                   // the tensor pipe idles ~600 cycles per round (event trace).  With it, everything above this line
                   // and the commits below overlap the other two issuers' bursts.
-                  mbar_wait_lean(turn_bar(me), turn_par);
+                  wait_lean(turn_bar(me), turn_par);
                   turn_par ^= 1u;
                   if (!leader) {
                     // (only the elected lane issues)
@@ -580,7 +575,13 @@ resnet_tc_sweep_kernel(const SwParams p) {
                     }
                   } else if (wrap_at == n) {
 #pragma unroll
-                    for (int k = 0; k < 3 * NKC; ++k) umma_f16_lohi2<true>(d1, al[k], a_hi, bl[k], desc_hi, id1);
+                    for (int k = 0; k < 3 * NKC; ++k) {
+                      umma_f16_lohi2<true>(d1, al[k], a_hi, bl[k], desc_hi, id1);
+                      if constexpr (SPLIT) {   // lo x hi, hi x lo (shared memory ends far below 256 KB: no carry out of the address fields)
+                        umma_f16_lohi2<true>(d1, al[k] + a_lo_off, a_hi, bl[k], desc_hi, id1);
+                        umma_f16_lohi2<true>(d1, al[k], a_hi, bl[k] + b_lo_off, desc_hi, id1);
+                      }
+                    }
                   } else {
                     // the window wraps around the ring: first wrap_at blocks at p0, the rest from slot 0
                     const uint32_t id2 = idesc0 + (uint32_t)(n - wrap_at) * idesc_blk;
@@ -589,6 +590,12 @@ resnet_tc_sweep_kernel(const SwParams p) {
                     for (int k = 0; k < 3 * NKC; ++k) {
                       umma_f16_lohi2<true>(d1, al[k], a_hi, bl[k], desc_hi, id1);
                       umma_f16_lohi2<true>(tmem_u, al[k], a_hi, bl[k] + bo2, desc_hi, id2);   // (weights end far below 256 KB: no carry out of the address field)
+                      if constexpr (SPLIT) {
+                        umma_f16_lohi2<true>(d1, al[k] + a_lo_off, a_hi, bl[k], desc_hi, id1);
+                        umma_f16_lohi2<true>(tmem_u, al[k] + a_lo_off, a_hi, bl[k] + bo2, desc_hi, id2);
+                        umma_f16_lohi2<true>(d1, al[k], a_hi, bl[k] + b_lo_off, desc_hi, id1);
+                        umma_f16_lohi2<true>(tmem_u, al[k], a_hi, bl[k] + b_lo_off + bo2, desc_hi, id2);
+                      }
                     }
                   }
                   if (leader) {
@@ -697,7 +704,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
               if (mine) {
                 const int row = it.s * 128 + q * 32 + lane;
                 ob.exists = true; ob.w = it.w; ob.s = it.s; ob.slot = esl; ob.par = epr;
-                ob.off = row >= H ? -1 : k32 ? (it.w * H + row) * 2 : it.w * col_pitch + col_base + row;
+                ob.off = row >= H ? -1 : k32 ? (it.w * H + row) * 2 : it.w * H + row;
               }
               // step the iterator, the ring slot and the owner
               ++it.o; it.w += d;
@@ -724,7 +731,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ob.slot * CP);
             // this lane's row of the staged skip column: [plane][128 rows][16 B]
             const uint32_t sk_addr = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT + (uint32_t)(q * 32 + lane) * 16u;
-            const uint32_t sk_plane = packed ? (uint32_t)PP * 16u : 2048u;
+            constexpr uint32_t sk_plane = 2048u;
             // k32: this lane's row, and whether its two 16-byte halves are stored swapped
             const uint32_t swl = (uint32_t)((p.dmax + q * 32 + lane) >> 2) & 1u;
             const uint32_t sk_addr32 = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT + (uint32_t)(q * 32 + lane) * 32u;
@@ -749,19 +756,31 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   // (single strip: H <= 128 rows = at most 16 lines per plane, one per lane)
                   const char* qb = reinterpret_cast<const char*>(bufQ);
                   const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(qb) & 127u);
-                  const uint32_t o0 = ((uint32_t)pl * (uint32_t)plane_stride + (uint32_t)(ob.w * col_pitch + col_base)) * 16u + mis;
+                  const uint32_t o0 = ((uint32_t)pl * (uint32_t)plane_stride + (uint32_t)(ob.w * H)) * 16u + mis;
                   const uint32_t a = ((o0 + 127u) & ~127u) + (uint32_t)j * 128u;
-                  if (a + 128u <= o0 + (uint32_t)(packed ? H : col_pitch) * 16u)   // (rows H .. col_pitch-1 of a column are never used)
+                  if (a + 128u <= o0 + (uint32_t)H * 16u)
                     asm volatile("discard.global.L2 [%0], 128;" ::"l"(qb + (a - mis)) : "memory");
                 }
               }
-              mbar_wait_sleepy(skfull_bar(g), eskpar); eskpar ^= 1u;
+              if constexpr (!SPLIT) { mbar_wait_sleepy(skfull_bar(g), eskpar); eskpar ^= 1u; }
             }
             // two accumulator register sets: the TMEM load of the next 16 channels is in flight during the math of these
             uint32_t v[2][16];
             tmem_ld16(tbase, v[0]);
 #pragma unroll
             for (int jj = 0; jj < NKC; ++jj) {
+              // SPLIT: the skip tensor (hi and lo rows of this lane's position, 32 B each) straight from L2 -- this mode's
+              // steps are three times as long, the latency hides behind the accumulator wait of the other groups' blocks
+              // and the shared memory of the staging slots holds the second weight set instead.  (.cg: the rows were
+              // stored by other warps of this CTA two pseudo-layers ago.)
+              uint4 skv[4] = {};
+              if constexpr (SPLIT && HAS_SKIP) {
+                if (valid) {
+                  const uint4* s_hi = bufP + jj * kc_stride + ob.off;
+                  const uint4* s_lo = bufP + (NKC + jj) * kc_stride + ob.off;
+                  skv[0] = ld_cg(s_hi); skv[1] = ld_cg(s_hi + 1); skv[2] = ld_cg(s_lo); skv[3] = ld_cg(s_lo + 1);
+                }
+              }
               tmem_ld_wait();
               tmem_st16_zero(tbase + 16 * jj);   // the next user of this ring slot accumulates from zero
               if (jj + 1 < NKC) {
@@ -773,7 +792,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 if (lane == 0) mbar_arrive(tempty_bar(ob.slot));   // all channels are in registers / stored, the slot is zero again
               }
               if (valid && !(DBG && (p.diag & 1))) {
-                uint4 ykeep = make_uint4(0u, 0u, 0u, 0u);
+                uint4 ykeep = make_uint4(0u, 0u, 0u, 0u), ykeep_lo = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                   float x[8], kc8[8];   // constants read at use (volatile: not hoisted into registers for the whole layer)
@@ -781,7 +800,19 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(kc8[4]), "=f"(kc8[5]), "=f"(kc8[6]), "=f"(kc8[7]) : "r"(kc_addr + (uint32_t)(64 * jj + 32 * hf + 16)));
 #pragma unroll
                   for (int e = 0; e < 8; ++e) x[e] = fmaxf(__uint_as_float(v[jj & 1][8 * hf + e]), 0.f) + kc8[e];
-                  if constexpr (HAS_SKIP) {
+                  if constexpr (HAS_SKIP && SPLIT) {
+                    // logical half hf of a row is stored at 16-byte slot hf ^ swl; skip = hi + lo
+                    const uint4 sh = (((uint32_t)hf ^ swl) != 0u) ? skv[1] : skv[0];
+                    const uint4 sl = (((uint32_t)hf ^ swl) != 0u) ? skv[3] : skv[2];
+                    const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&sh);
+                    const __nv_bfloat162* pl2 = reinterpret_cast<const __nv_bfloat162*>(&sl);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 fh = __bfloat1622float2(ph[e]), fl = __bfloat1622float2(pl2[e]);
+                      x[2 * e] += fh.x + fl.x;
+                      x[2 * e + 1] += fh.y + fl.y;
+                    }
+                  } else if constexpr (HAS_SKIP) {
                     uint4 sv;   // 8 channels of the skip tensor at this position (plane 2 jj + hf)
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(sv.x), "=r"(sv.y), "=r"(sv.z), "=r"(sv.w)
                                  : "r"(k32 ? sk_addr32 + (uint32_t)jj * 4096u + (((uint32_t)hf ^ swl) << 4)
@@ -802,7 +833,21 @@ resnet_tc_sweep_kernel(const SwParams p) {
                     __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&yo);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) yb[e] = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-                    if constexpr (k32) {
+                    if constexpr (SPLIT) {
+                      // the residual x - float(hi), again as bf16: hi + lo carries 16 mantissa bits of x
+                      uint4 yl;
+                      __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&yl);
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        const float2 fh = __bfloat1622float2(yb[e]);
+                        lb[e] = __floats2bfloat162_rn(x[2 * e] - fh.x, x[2 * e + 1] - fh.y);
+                      }
+                      if (hf == 0) { ykeep = yo; ykeep_lo = yl; }
+                      else {
+                        st_hint256(y_out + jj * kc_stride + ob.off, swl ? yo : ykeep, swl ? ykeep : yo, pol_out);
+                        st_hint256(y_out + (NKC + jj) * kc_stride + ob.off, swl ? yl : ykeep_lo, swl ? ykeep_lo : yl, pol_out);
+                      }
+                    } else if constexpr (k32) {
                       // both halves of this row's 32 bytes in ONE store (16-byte stores at a 32-byte stride would write
                       // every sector in two halves); which half comes first follows the row's swizzle bit
                       if (hf == 0) ykeep = yo;
@@ -828,7 +873,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
           // warps have finished reading the previous one, i.e. two block periods before it is needed: no L2 latency on
           // the epilogue's critical path and no prefetch registers (they hold a second accumulator set instead).
           auto stage_skip = [&](const Own& ob) {
-            if constexpr (HAS_SKIP) {
+            if constexpr (HAS_SKIP && !SPLIT) {
               asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");   // the group's four warps are done with the slot
               if (k32) {
                 if (q == 0 && ob.exists && elect_one()) {   // [K chunk][128 rows][32 B]
@@ -840,16 +885,10 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   for (int kc = 0; kc < NKC; ++kc)
                     bulk_load_hint(d0 + (uint32_t)kc * 4096u, src + kc * kc_stride, bytes, skfull_bar(g), pol_keep);
                 }
-              } else if (packed) {
-                if (q == 0 && ob.exists && elect_one()) {   // planes PP rows apart, one copy (host plan: PP <= 128)
-                  const uint32_t bytes = (uint32_t)(NP * PP) * 16u;
-                  mbar_expect_tx(skfull_bar(g), bytes);
-                  bulk_load_hint(sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT, bufP + (int64_t)ob.w * COLP + p.dmax, bytes, skfull_bar(g), pol_keep);
-                }
               } else if (q == 0 && ob.exists && elect_one()) {
                 const int rows = H - ob.s * 128 < 128 ? H - ob.s * 128 : 128;
                 mbar_expect_tx(skfull_bar(g), (uint32_t)(NP * rows * 16));
-                const uint4* src = bufP + (int64_t)ob.w * col_pitch + ob.s * 128;
+                const uint4* src = bufP + (int64_t)ob.w * H + ob.s * 128;
                 const uint32_t d0 = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT;
 #pragma unroll
                 for (int pl = 0; pl < NP; ++pl)

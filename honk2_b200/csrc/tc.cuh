@@ -12,12 +12,13 @@ void tc_resnet_destroy(TcResNet* p);
 // the caller already derived from running_mean / running_var.
 int tc_resnet_set_weights(TcResNet* p, const kws_resnet_weights& w, float* const* bn_scale,
                           float* const* bn_shift, cudaStream_t st);
-size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int chunk);
+// split: the "bf16x3" precision (operands as bf16 pairs hi + lo, three MMAs per product) instead of plain bf16
+size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int chunk, bool split);
 int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, float* logits, void* ws,
-                      size_t ws_bytes, int chunk, LaunchProfiler* prof, cudaStream_t st);
+                      size_t ws_bytes, int chunk, bool split, LaunchProfiler* prof, cudaStream_t st);
 
 // Which kernel a bf16 forward of a [B][T][F] batch runs: "resnet_tc_sweep_kernel", "resnet_tc_fused_kernel",
 // "conv3x3_tc_kernel" (layer per launch) or "unsupported".
-const char* tc_resnet_kernel_path(const TcResNet* p, int T, int F);
+const char* tc_resnet_kernel_path(const TcResNet* p, int T, int F, bool split);
 
 }  // namespace kws

@@ -64,34 +64,64 @@ def evaluate_waves(model, audio_processor, waves, targets=None, batch_size=8192,
 
 
 class HostPipeline(object):
-    """waveforms in (pinned) HOST memory -> logits in (pinned) HOST memory, with the host->device
-    copies of sub-batch k+1 overlapped with the kernels of sub-batch k (two staging buffers, one
-    copy stream).  This is the e2e form of the collate + forward loop: the reference copies each
-    batch synchronously from pageable memory (`data.to(device)`, run/test.py:23)."""
+    """waveforms in (pinned) HOST memory -> logits in (pinned) HOST memory, with the host->device copies of the next
+    sub-batches overlapped with the kernels of the current one (``slots`` staging buffers, one copy stream).  This is
+    the e2e form of the collate + forward loop: the reference copies each batch synchronously from pageable memory
+    (`data.to(device)`, run/test.py:23).
 
-    def __init__(self, model, audio_processor, n_samples, sub_batch=2048, device=None):
+    ``__call__`` returns a CUDA event recorded after the last device->host copy of the call: the caller owns
+    ``host_logits`` again once ``event.synchronize()`` returns (``sync=True``, the default, does that before
+    returning).  Calls may be issued back to back without synchronising: a staging slot is only refilled after the
+    forward that read it has finished (``consumed`` events, also across calls)."""
+
+    def __init__(self, model, audio_processor, n_samples, sub_batch=2048, device=None, slots=3):
         self.model, self.ap = model, audio_processor
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.sub = int(sub_batch)
-        self.stage = [torch.empty((self.sub, n_samples), dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.slots = max(2, int(slots))
+        self.stage = [torch.empty((self.sub, n_samples), dtype=torch.float32, device=self.device)
+                      for _ in range(self.slots)]
+        self.dev_logits = [torch.empty((self.sub, model.n_labels), dtype=torch.float32, device=self.device)
+                           for _ in range(self.slots)]
         self.copy_stream = torch.cuda.Stream(self.device)
-        self.copied = [torch.cuda.Event() for _ in range(2)]
-        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.copied = [torch.cuda.Event() for _ in range(self.slots)]
+        self.consumed = [torch.cuda.Event() for _ in range(self.slots)]
+        self._next = 0   # staging slot of the next sub-batch (keeps rotating across calls)
 
-    def __call__(self, host_waves, host_logits):
+    def __call__(self, host_waves, host_logits, sync=True):
         n = host_waves.shape[0]
         main = torch.cuda.current_stream(self.device)
         spans = [(b0, min(n, b0 + self.sub)) for b0 in range(0, n, self.sub)]
+        done = torch.cuda.Event()
         with torch.no_grad():
-            for k, (b0, b1) in enumerate(spans):
-                slot = k & 1
+            # copies run `slots - 1` sub-batches ahead of the kernels
+            issued = 0
+
+            def issue_copy():
+                nonlocal issued
+                b0, b1 = spans[issued]
+                slot = (self._next + issued) % self.slots
                 with torch.cuda.stream(self.copy_stream):
-                    if k >= 2:
-                        self.copy_stream.wait_event(self.consumed[slot])    # staging buffer is free again
+                    # the forward that last read this slot (in this call or an earlier one) has finished
+                    # (waiting on an event that was never recorded is a no-op)
+                    self.copy_stream.wait_event(self.consumed[slot])
                     self.stage[slot][: b1 - b0].copy_(host_waves[b0:b1], non_blocking=True)
                     self.copied[slot].record(self.copy_stream)
+                issued += 1
+
+            while issued < min(self.slots - 1, len(spans)):
+                issue_copy()
+            for k, (b0, b1) in enumerate(spans):
+                if issued < len(spans):
+                    issue_copy()
+                slot = (self._next + k) % self.slots
                 main.wait_event(self.copied[slot])
-                logits = self.model.forward_wave(self.stage[slot][: b1 - b0], self.ap)
+                logits = self.model.forward_wave(self.stage[slot][: b1 - b0], self.ap,
+                                                 out=self.dev_logits[slot][: b1 - b0])
                 self.consumed[slot].record(main)
                 host_logits[b0:b1].copy_(logits, non_blocking=True)
-        return host_logits
+            done.record(main)
+        self._next = (self._next + len(spans)) % self.slots
+        if sync:
+            done.synchronize()
+        return done

@@ -10,10 +10,41 @@ from .class_registry import register_cls
 from .dist import all_reduce_counts
 
 
+class _MetricType(object):
+    """Stand-in for the reference's ``MetricType`` enum (/root/reference/metric/metric_utils.py:5-7) that compares equal
+    to it by ``.value``: ``criterion.get_type() == MetricType.MACRO`` (run/train.py:104) and ``collect_metrics``
+    (metric_utils.py:42-45) put OUR object on the left of ``==``, so both work with the reference's own enum."""
+    __slots__ = ("name", "value")
+
+    def __init__(self, value):
+        self.name = self.value = value
+
+    def __eq__(self, other):
+        return getattr(other, "value", other) == self.value
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash(self.value)
+
+    def __repr__(self):
+        return f"<MetricType.{self.name}: {self.value!r}>"
+
+
+class MetricType(object):
+    MACRO = _MetricType("MACRO")
+    MICRO = _MetricType("MICRO")
+
+
 @register_cls('metric.Acc')
 class Acc(object):
-    def __init__(self):
-        self._counts = None  # device int64 [correct, total]
+    def __init__(self, counts=None):
+        """counts: optional device int64[2] to accumulate into (e.g. a view of a collective's send buffer)."""
+        self._counts = counts  # device int64 [correct, total]
+
+    def get_type(self):       # MicroMetric.get_type (metric_utils.py:23-28): a scalar metric, reported as is
+        return MetricType.MACRO
 
     def accumulate(self, output, target, return_pred=False):
         if not output.is_cuda:
@@ -75,9 +106,8 @@ class PerClassAcc(object):
     def __init__(self):
         self._counts = None   # device int64 [n_labels][2] = (total, correct)
 
-    def get_type(self):       # MacroMetric.get_type (metric_utils.py:33-38): re-keyed by label in collect_metrics
-        from enum import Enum
-        return Enum("MetricType", {"MACRO": "MACRO", "MICRO": "MICRO"}).MICRO
+    def get_type(self):       # MacroMetric.get_type (metric_utils.py:31-36): re-keyed by label in collect_metrics
+        return MetricType.MICRO
 
     def accumulate(self, output, target):
         assert output.shape[0] == len(target)
@@ -106,8 +136,11 @@ class PerClassAcc(object):
 @register_cls('loss_fn.ce_loss')
 def ce_loss(output, target):
     """``loss_fn.ce_loss`` (/root/reference/loss_function.py:7-9): mean categorical cross entropy of raw logits,
-    as a 0-dim tensor on the logits' device; computed by kws_eval_accumulate (no host sync).  Inference only: the
-    result carries no autograd graph."""
+    as a 0-dim tensor on the logits' device; computed by kws_eval_accumulate (no host sync).  When the logits carry
+    an autograd graph (run/train.py:142-143 calls ``loss.backward()``) or live on the CPU, this is the reference's own
+    ``nn.CrossEntropyLoss`` -- training is outside the native path."""
+    if output.requires_grad or not output.is_cuda:
+        return torch.nn.functional.cross_entropy(output, target)
     output = output.detach().float().contiguous()
     target = target.to(output.device, torch.int64).contiguous()
     s = torch.zeros(1, dtype=torch.float64, device=output.device)

@@ -10,7 +10,10 @@ reference signature -- ``x`` float32 ``[B, T, F]`` -> raw logits ``[B, n_labels]
 ``kws_model_forward``; the torch submodules only hold the parameters.  There is no CPU or
 eager fallback: a CPU tensor, training mode, or a missing library raises.
 
-Optional config key (default keeps old configs working): ``"precision": "fp32" | "bf16"``.
+Optional config key (default keeps old configs working): ``"precision": "fp32" | "bf16" | "bf16x3"``
+(fp32 = CUDA-core FFMA reference mode; bf16 = tcgen05 tensor cores with bf16 operands; bf16x3 = tensor cores with
+split-bf16 operands -- activations and weights as hi + lo bf16 pairs, three MMAs per product, fp32 accumulate --
+which meets the fp32 tolerance at tensor-core speed).
 """
 import ctypes as C
 
@@ -71,7 +74,7 @@ class BaseModel(nn.Module):
                 # the contiguous fp32 staging copies made by _upload die when it returns
                 torch.cuda.current_stream(device).synchronize()
             st["stamp"] = stamp
-        chunk = (self.chunk.get("fp32", 0), self.chunk.get("bf16", 0))
+        chunk = tuple(self.chunk.get(name, 0) for name in _native.PRECISIONS)
         if st["chunk"] != chunk:
             for name, prec in _native.PRECISIONS.items():
                 _native.check(lib.kws_model_set_chunk(st["handle"], prec, int(self.chunk.get(name, 0))),
@@ -103,12 +106,20 @@ class BaseModel(nn.Module):
             x = x.float()
         return x.contiguous()
 
-    def forward(self, x):
+    def _logits_out(self, out, B, device):
+        if out is None:
+            return torch.empty((B, self.n_labels), dtype=torch.float32, device=device)
+        if out.shape != (B, self.n_labels) or out.dtype != torch.float32 or not out.is_contiguous() \
+                or out.device != device:
+            raise ValueError("out must be a contiguous float32 [B, n_labels] tensor on the input's device")
+        return out
+
+    def forward(self, x, out=None):
         x = self._check_input(x, 3)
         B, T, F = x.shape
         lib, st = self._state(x.device)
         prec = self._precision_id()
-        logits = torch.empty((B, self.n_labels), dtype=torch.float32, device=x.device)
+        logits = self._logits_out(out, B, x.device)
         if B == 0:
             return logits
         with torch.cuda.device(x.device):
@@ -123,15 +134,15 @@ class BaseModel(nn.Module):
                           "kws_model_forward")
         return logits
 
-    def forward_wave(self, waves, audio_processor):
+    def forward_wave(self, waves, audio_processor, out=None):
         """Fused collate + forward: CUDA float32 waveforms [B, N] -> logits [B, n_labels]
-        (data_loader/audio_data_loader.py:26-29 followed by model(x))."""
+        (data_loader/audio_data_loader.py:26-29 followed by model(x)).  `out`: optional preallocated logits."""
         waves = self._check_input(waves, 2)
         B, N = waves.shape
         lib, st = self._state(waves.device)
         fe = audio_processor._frontend(waves.device)
         prec = self._precision_id()
-        logits = torch.empty((B, self.n_labels), dtype=torch.float32, device=waves.device)
+        logits = self._logits_out(out, B, waves.device)
         if B == 0:
             return logits
         with torch.cuda.device(waves.device):
@@ -152,10 +163,13 @@ class BaseModel(nn.Module):
         return 0 if st is None else int(_native.load().kws_model_last_launches(st["handle"]))
 
     def __del__(self):
+        # (never dlopen from a destructor: a model that was only ever used on the CPU side -- state_dict, parameter
+        # counts -- must not map the native library into its process)
         try:
-            lib = _native.load()
-            for st in self._native_state.values():
-                lib.kws_model_destroy(st["handle"])
+            lib = _native.loaded()
+            if lib is not None:
+                for st in self._native_state.values():
+                    lib.kws_model_destroy(st["handle"])
         except Exception:
             pass
 
@@ -232,41 +246,25 @@ class CNN(BaseModel):
         self.config = {k: config[k] for k in ("time", "frequency", "conv_0", "pool_0", "conv_1", "pool_1",
                                               "lin_0", "dnn_0", "dnn_1") if k in config}
 
-        time = config['time']
-        frequency = config['frequency']
-
-        conv_in_channels = 1
-        conv_out_channels = config["conv_0"]["out_channels"]
-        conv_kernel_size = config["conv_0"]["kernel_size"]
-        conv_stride = config["conv_0"]["stride"]
-        tensor_size = [conv_in_channels, time, frequency]
-        self.layers["conv_0"] = nn.Conv2d(conv_in_channels, conv_out_channels, conv_kernel_size, stride=conv_stride)
-        tensor_size = [conv_out_channels] + calculate_conv_output_size(tensor_size[1:], conv_kernel_size,
-                                                                       stride=conv_stride)
-        pool_kernel_size = config["pool_0"]["kernel_size"]
-        self.layers["pool_0"] = nn.MaxPool2d(pool_kernel_size)
-        tensor_size = [conv_out_channels] + calculate_pool_output_size(tensor_size[1:], pool_kernel_size)
-
-        if "conv_1" in config:
-            conv_in_channels = conv_out_channels
-            conv_out_channels = config["conv_1"]["out_channels"]
-            conv_kernel_size = config["conv_1"]["kernel_size"]
-            conv_stride = config["conv_1"]["stride"]
-            self.layers["conv_1"] = nn.Conv2d(conv_in_channels, conv_out_channels, conv_kernel_size,
-                                              stride=conv_stride)
-            tensor_size = [conv_out_channels] + calculate_conv_output_size(tensor_size[1:], conv_kernel_size,
-                                                                           stride=conv_stride)
-            pool_kernel_size = config["pool_1"]["kernel_size"]
-            self.layers["pool_1"] = nn.MaxPool2d(pool_kernel_size)
-            tensor_size = [conv_out_channels] + calculate_pool_output_size(tensor_size[1:], pool_kernel_size)
-
-        dnn_in_features = int(np.prod(tensor_size))
+        # Same submodules, same order and same RNG consumption as the reference constructor (cnn.py:14-73), so that
+        # state_dict keys and default initialisation agree: [conv_i, pool_i]* -> lin_0 / dnn_0 / dnn_1 -> lin_1.
+        channels, size = 1, [config["time"], config["frequency"]]
+        for i in (0, 1):
+            if f"conv_{i}" not in config:
+                break
+            spec = config[f"conv_{i}"]
+            self.layers[f"conv_{i}"] = nn.Conv2d(channels, spec["out_channels"], spec["kernel_size"], stride=spec["stride"])
+            channels = spec["out_channels"]
+            size = calculate_conv_output_size(size, spec["kernel_size"], stride=spec["stride"])
+            pool = config[f"pool_{i}"]["kernel_size"]
+            self.layers[f"pool_{i}"] = nn.MaxPool2d(pool)
+            size = calculate_pool_output_size(size, pool)
+        width = int(channels * np.prod(size))
         for name in ("lin_0", "dnn_0", "dnn_1"):
             if name in config:
-                dnn_out_features = config[name]["out_features"]
-                self.layers[name] = nn.Linear(dnn_in_features, dnn_out_features)
-                dnn_in_features = dnn_out_features
-        self.layers["lin_1"] = nn.Linear(dnn_in_features, config["n_labels"])
+                self.layers[name] = nn.Linear(width, config[name]["out_features"])
+                width = config[name]["out_features"]
+        self.layers["lin_1"] = nn.Linear(width, config["n_labels"])
         self.layers["dropout"] = nn.Dropout(config["dropout_prob"])
         self.activations = nn.ModuleDict({"relu": nn.ReLU()})
 

@@ -64,8 +64,9 @@ def evaluate_stream(model, audio_processor, stream, window_size=16000, shift_siz
     if not (isinstance(stream, torch.Tensor) and stream.is_cuda and stream.dim() == 1):
         raise ValueError("evaluate_stream expects a 1-D CUDA tensor")
     n = n_stream_windows(stream.numel(), window_size, shift_size)
+    from .metric import Acc
     logits = []
-    correct = torch.zeros((), dtype=torch.int64, device=stream.device)
+    acc = Acc()
     tgt = None
     if targets is not None:
         tgt = torch.as_tensor(np.asarray(targets), dtype=torch.int64, device=stream.device)
@@ -78,8 +79,8 @@ def evaluate_stream(model, audio_processor, stream, window_size=16000, shift_siz
             y = model(feats)
             logits.append(y)
             if tgt is not None:
-                correct += (y.argmax(dim=1) == tgt[first:first + count]).sum()
+                acc.accumulate(y, tgt[first:first + count])     # kws_acc_accumulate: counts stay on the device
     out = torch.cat(logits) if logits else torch.empty((0, 0), device=stream.device)
     if tgt is None:
         return out
-    return out, {"correct": int(correct.item()), "total": n}
+    return out, {"correct": acc.counts()[0], "total": n}

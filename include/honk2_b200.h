@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define KWS_ABI_VERSION 1
+#define KWS_ABI_VERSION 2
 
 enum {
   KWS_OK = 0,
@@ -32,7 +32,10 @@ enum {
 
 enum {
   KWS_FP32 = 0,  /* CUDA-core FFMA path, fp32 storage and accumulate (parity mode) */
-  KWS_BF16 = 1   /* tcgen05 tensor-core path: bf16 operands, fp32 TMEM accumulate */
+  KWS_BF16 = 1,  /* tcgen05 tensor-core path: bf16 operands, fp32 TMEM accumulate */
+  KWS_BF16X3 = 2 /* tcgen05 tensor-core path with split-bf16 operands: every activation and weight is a bf16 pair
+                    hi + lo (16 mantissa bits), every product three MMAs (hi*hi + hi*lo + lo*hi), fp32 accumulate:
+                    meets the fp32 tolerance (1e-3 of the logit scale, identical argmax) at tensor-core speed */
 };
 
 typedef struct kws_frontend kws_frontend_t;

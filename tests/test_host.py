@@ -49,7 +49,8 @@ def test_registry_contract():
 
 
 def test_install_into_foreign_registry():
-    """The plug-in hook: our classes re-registered into another registry (honk2's own)."""
+    """The plug-in hook: our classes re-registered into another registry (honk2's own).  Only model.* by default:
+    run_utils.py is imported by the training script too."""
     other = Registry()
 
     def other_register(identifier):
@@ -57,24 +58,64 @@ def test_install_into_foreign_registry():
             other.add(identifier, cls)
             return cls
         return deco
-    honk2_b200.install_into(other_register)
+    done = honk2_b200.install_into(other_register)
+    assert sorted(done) == ["model.CNN", "model.ResNet"]
     assert other.get("model.ResNet") is honk2_b200.ResNet and other.get("model.CNN") is honk2_b200.CNN
-    assert other.get("metric.Acc") is not None or True
+    assert other.get("metric.Acc") is None and other.get("loss_fn.ce_loss") is None
+    done = honk2_b200.install_into(other_register, prefixes=("metric.", "loss_fn.", "data_loader."))
+    assert sorted(done) == ["data_loader.AudioDataLoader", "loss_fn.ce_loss", "metric.Acc", "metric.PerClassAcc"]
+    assert other.get("metric.Acc") is honk2_b200.metric.Acc
 
 
 @pytest.mark.skipif(not reference_loader.available(), reason="reference checkout not present")
 def test_install_into_reference_registry_overrides_model_classes():
     ref_find = reference_loader.load()
     import utils as ref_utils
-    original = {k: ref_find(k) for k in ("model.ResNet", "model.CNN")}
+    from metric.metric_utils import MetricType, collect_metrics    # (imports, hence registers, the reference's metrics)
+    touched = ("model.ResNet", "model.CNN", "metric.Acc", "metric.PerClassAcc", "loss_fn.ce_loss",
+               "data_loader.AudioDataLoader")
+    original = {k: ref_find(k) for k in touched}
     try:
-        honk2_b200.install_into(ref_utils.register_cls)
+        assert sorted(honk2_b200.install_into(ref_utils.register_cls)) == ["model.CNN", "model.ResNet"]
         kind, cfg = model_config("res8")
         m = ref_find(f"model.{kind}")(cfg)           # run/test.py:61-64
         assert isinstance(m, honk2_b200.ResNet)
+        assert ref_find("metric.Acc") is original["metric.Acc"]        # metrics and loss stay the reference's
+        # opting in to the device-resident metrics keeps the reference's contracts
+        honk2_b200.install_into(ref_utils.register_cls, prefixes=("metric.", "loss_fn."))
+        acc, pca = ref_find("metric.Acc")(), ref_find("metric.PerClassAcc")()
+        assert isinstance(acc, honk2_b200.metric.Acc)
+        assert acc.get_type() == MetricType.MACRO                        # run/train.py:104
+        assert pca.get_type() == MetricType.MICRO
+        acc.get_metric = lambda: 0.5
+        pca.get_metric = lambda: {0: 1.0, 1: 0.25}
+        out = collect_metrics({"Acc": acc, "PerClassAcc": pca}, ["yes", "no"])    # metric_utils.py:39-52
+        assert out == {"metric_Acc": 0.5, "metric_PerClassAcc": {"yes": 1.0, "no": 0.25}}
+        # the loss keeps an autograd graph when the logits have one (run/train.py:142-143)
+        logits = torch.randn(4, 3, requires_grad=True)
+        loss = ref_find("loss_fn.ce_loss")(logits, torch.tensor([0, 1, 2, 1]))
+        loss.backward()
+        assert logits.grad is not None and torch.isfinite(logits.grad).all()
+        assert torch.allclose(loss, torch.nn.functional.cross_entropy(logits, torch.tensor([0, 1, 2, 1])))
     finally:
         for k, v in original.items():
-            ref_utils.register_cls(k)(v)
+            if v is not None:
+                ref_utils.register_cls(k)(v)
+
+
+def test_models_do_not_load_the_native_library_on_the_cpu_side(tmp_path):
+    """Constructing a model, reading its state_dict and deleting it must not dlopen the library (bench.py's CPU arm
+    and checkpoint tools touch only that surface)."""
+    code = ("import honk2_b200, gc\n"
+            "from honk2_b200 import _native\n"
+            "m = honk2_b200.build_model('res8'); sd = m.state_dict(); n = m.num_params(); del m; gc.collect()\n"
+            "ap = honk2_b200.AudioProcessor(); del ap; gc.collect()\n"
+            "assert _native.loaded() is None\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libhonk2_b200' not in maps, 'native library was mapped'\n"
+            "print('ok', n)\n")
+    r = subprocess.run([os.sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok 110307"), r.stdout + r.stderr
 
 
 # ---- size calculators (utils/torch_utils.py:29-65) ----------------------------------------------
@@ -236,7 +277,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     for n in names:
         assert hasattr(native_lib, n), f"{n} is declared in include/honk2_b200.h but not exported"
     assert set(names) == set(_native.SIGNATURES), "ctypes table and header disagree"
-    assert native_lib.kws_abi_version() == 1
+    assert native_lib.kws_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_library_is_sm100a_only():
