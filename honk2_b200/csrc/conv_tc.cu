@@ -1244,7 +1244,7 @@ static int tc_encode_map(const void* base, int64_t planes, int H, int W, const T
 // ---- whole-network persistent kernel: geometry, shared-memory plan, device tables ----------------
 struct TcFusedPlan {
   bool ok = false, split = false;
-  int Hpad = 0, n_slots = 0, smem_total = 0;
+  int Hpad = 0, n_slots = 0, smem_total = 0, n_stages = 0;
   int w_off[2] = {0, 0}, ring_off = 0, slot_bytes = 0;
   std::vector<TcGeom> geoms;
 };
@@ -1257,7 +1257,7 @@ static TcFusedPlan tc_fused_plan(const TcResNet* p, int H, int W, bool split) {
   f.n_slots = p->n_sms;
   f.split = split;
   const int w_bytes = (split ? 2 : 1) * 9 * p->NKC * 2 * p->CP * 16;
-  f.w_off[0] = 5120;   // control block: barriers, pooled sums, constants, layer descriptors, conv_0 weights
+  f.w_off[0] = 6144;   // control block: barriers, constants, layer descriptors, conv_0 weights, pooled sums
   f.w_off[1] = split ? f.w_off[0] : f.w_off[0] + round_up(w_bytes, 128);   // (split: one buffer for both weight sets)
   f.ring_off = round_up(f.w_off[1] + w_bytes, 1024);
   for (int i = 1; i <= c.n_layers; ++i) {
@@ -1268,8 +1268,10 @@ static TcFusedPlan tc_fused_plan(const TcResNet* p, int H, int W, bool split) {
     f.slot_bytes = std::max(f.slot_bytes, round_up(g.stage_bytes, 128));
     f.geoms.push_back(g);
   }
-  f.smem_total = f.ring_off + kFusedStages * f.slot_bytes + 4096;
-  f.ok = f.smem_total <= 227 * 1024;
+  // as many ring slots as fit (large dilations stage three row-blocks per tile: fewer, larger slots)
+  f.n_stages = std::min(kFusedStages, (227 * 1024 - 4096 - f.ring_off) / std::max(f.slot_bytes, 1));
+  f.smem_total = f.ring_off + f.n_stages * f.slot_bytes + 4096;
+  f.ok = f.n_stages >= 2;
   return f;
 }
 
@@ -1335,7 +1337,7 @@ static int tc_fused_forward(TcResNet* p, const TcFusedPlan& f, const float* feat
     q.ph = c.pool_h > 0 ? c.pool_h : 1; q.pw = c.pool_w > 0 ? c.pool_w : 1;
     q.H = H; q.W = W; q.Hpad = f.Hpad;
     q.smem_w_off[0] = f.w_off[0]; q.smem_w_off[1] = f.w_off[1];
-    q.smem_ring_off = f.ring_off; q.ring_slot_bytes = f.slot_bytes;
+    q.smem_ring_off = f.ring_off; q.ring_slot_bytes = f.slot_bytes; q.n_stages = f.n_stages;
     q.l2_policy = p->l2_policy;
     p->fused_smem = f.smem_total;
     p->fused_key = key;

@@ -25,7 +25,7 @@
 
 namespace kws {
 
-constexpr int kFusedStages = 4;     // ring slots, fixed for all layers (slot size varies per layer)
+constexpr int kFusedStages = 4;     // most ring slots (the plan takes fewer, down to 2, when a layer's staged tile is large)
 constexpr int kFusedMaxLayers = 64;
 
 struct TcLayerDesc {
@@ -52,6 +52,7 @@ struct TcFusedParams {
   int64_t B;
   int n_layers, C, n_labels, T, F, ph, pw, H, W, Hpad;
   int smem_w_off[2], smem_ring_off, ring_slot_bytes;
+  int n_stages;       // ring slots in use (2 .. kFusedStages)
   long long* debug;   // optional [16] cycle counters written by CTA 0's first issuer thread (nullptr = off)
   int l2_policy;   // 1: buffer P (read twice, rewritten in place) evict_last, buffer Q (write once, read once) evict_first
 };
@@ -72,10 +73,10 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
   constexpr int MAXU = (MAXMT + kTcIssuers - 1) / kTcIssuers;
   extern __shared__ __align__(1024) unsigned char smem[];
 
-  // ---- shared memory carve-up (first 4 KB: control)
+  // ---- shared memory carve-up (first 6 KB: control)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);    // full[4], empty[4], tfull[2], tempty[2], wfull[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 128);
-  float* s_pool = reinterpret_cast<float*>(smem + 256);                 // [CP]   pooled sums of the current utterance
+  float* s_pool = reinterpret_cast<float*>(smem + 4608);                // [4 lane quarters][CP] pooled sums of the current utterance
   float* s_kconst = reinterpret_cast<float*>(smem + 512);               // [2][CP]
   TcLayerDesc* s_layer = reinterpret_cast<TcLayerDesc*>(smem + 1024);   // [2]
   float* s_w0 = reinterpret_cast<float*>(smem + 1536);                  // [CP][12] conv_0 weights (<= 64*12*4 = 3 KB)
@@ -114,7 +115,6 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
     s_w0[i] = (k < 9 && c < p.C) ? p.conv0_w[c * 9 + k] : 0.f;
   }
   for (int i = threadIdx.x; i < CP; i += kThreads) {
-    s_pool[i] = 0.f;
     if (n_seq > 0) s_kconst[i] = p.layers[0].kconst[i];
   }
   tc_fence_before();
@@ -319,7 +319,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
                   else
                     tma_load_5d(sbase + half * g.slab_bytes + bx * g.box_stride, map, full_bar(stage), 0, -g.dpad,
                                 r0 + g.h_start[bx], ph, (int)blockIdx.x * NPX + 2 * kc + half);
-              if (++stage == kFusedStages) { stage = 0; phase ^= 1; }
+              if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
           }
         }
@@ -390,7 +390,7 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
             }
             __syncwarp();
             if (dbg) { const long long t = clock64(); dbg_issue += t - dbg_t; dbg_t = t; }
-            if (++stage == kFusedStages) { stage = 0; phase ^= 1; }
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
           }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
@@ -510,13 +510,14 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
           if (acc == 0) acc_phase ^= 1;
         }
         if (last) {
-          // fused global mean (resnet.py:57-58): warp-reduce the 32 positions, one shared atomic per channel
+          // fused global mean (resnet.py:57-58): warp-reduce the 32 positions; every warp leaves its share in its own
+          // slot (no atomics: the logits add the four lane quarters in a fixed order => bit-reproducible)
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             float sum = psum[c];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == c) atomicAdd(s_pool + 16 * j + c, sum);
+            if (lane == c) s_pool[q * CP + 16 * j + c] = sum;
           }
         }
         __threadfence();
@@ -533,13 +534,13 @@ resnet_tc_fused_kernel(const TcFusedParams p) {
         const float inv = 1.f / (float)(p.H * p.W);
         float v = __ldg(p.out_b + lb);
         // s_pool holds sums of z = x - mean; the BatchNorm output mean is z_mean / sigma (resnet.py:55-58)
-        for (int c = 0; c < p.C; ++c)
-          v = fmaf(s_pool[c] * inv * __ldg(p.last_scale + c), __ldg(p.out_w + lb * p.C + c), v);
+        for (int c = 0; c < p.C; ++c) {
+          const float pooled = (s_pool[c] + s_pool[CP + c]) + (s_pool[2 * CP + c] + s_pool[3 * CP + c]);
+          v = fmaf(pooled * inv * __ldg(p.last_scale + c), __ldg(p.out_w + lb * p.C + c), v);
+        }
         p.logits[b * p.n_labels + lb] = v;
       }
-      __syncthreads();
-      for (int i = threadIdx.x; i < CP; i += kThreads) s_pool[i] = 0.f;
-      // the next writer of s_pool is many barriers away (last layer of the next utterance)
+      // (s_pool is rewritten by the last layer of the next utterance, many barriers away)
     }
   }
 

@@ -74,10 +74,10 @@ constexpr int kSwSkipSlots = 4;     // skip-tensor staging (shared memory): one 
 constexpr int kSwBarSkFull = kSwBarTurn + 8 * 4;               // [kSwSkipSlots]
 constexpr int kSwBarCol = kSwBarSkFull + 8 * kSwSkipSlots;     // [2][kSwMaxW]  column stored by the owning epilogue warps
 constexpr int kSwTmemSlot = kSwBarCol + 8 * 2 * kSwMaxW;       // u32
-constexpr int kSwPool = round_up(kSwTmemSlot + 4, 128);        // [64] f32 pooled sums
-constexpr int kSwKc = kSwPool + 256;                           // [1 + n_layers][CP] f32 epilogue constants (row 0 = conv_0 = zeros)
-constexpr int kSwKcBytes = 7168;
-constexpr int kSwCtrlBytes = round_up(kSwKc + kSwKcBytes, 1024);
+constexpr int kSwKc = round_up(kSwTmemSlot + 4, 128);          // [1 + n_layers][CP] f32 epilogue constants (row 0 = conv_0 = zeros)
+constexpr int kSwKcBytes = 6144;
+constexpr int kSwPool = kSwKc + kSwKcBytes;                    // [12 epilogue warps][48] f32: every warp's share of the pooled sums
+constexpr int kSwCtrlBytes = round_up(kSwPool + 12 * 48 * 4, 1024);
 // (epilogue warp group g = warp / 4, one warp per TMEM lane quarter, owns the blocks = g mod NKC: there are NKC groups)
 
 struct SwParams {
@@ -192,7 +192,6 @@ resnet_tc_sweep_kernel(const SwParams p) {
     uint4* dst = reinterpret_cast<uint4*>(smem + p.smem_c0w_off);
     for (int i = threadIdx.x; i < (3 * W_SLAB) / 16; i += sw_threads(NKC)) dst[i] = src[i];
   }
-  for (int i = threadIdx.x; i < CP; i += sw_threads(NKC)) s_pool[i] = 0.f;
   {   // epilogue constants of every pseudo-layer, read from shared memory at use
       // (the host plan guarantees (1 + n_layers) * CP * 4 <= kSwKcBytes)
     float* s_kc = reinterpret_cast<float*>(smem + kSwKc);
@@ -905,13 +904,15 @@ resnet_tc_sweep_kernel(const SwParams p) {
           }
           if (pending_w >= 0) publish(pending_w);
           if constexpr (LAST) {
-            // fused global mean (resnet.py:57-58): warp-reduce the 32 rows, one shared atomic per channel
+            // fused global mean (resnet.py:57-58): warp-reduce the 32 rows; every warp leaves ITS share of every channel
+            // in its own row of s_pool (no atomics: the logits below add the rows in a fixed order, so repeated
+            // launches agree bit for bit)
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
               float sum = psum[c];
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-              if (lane == (c & 31)) atomicAdd(s_pool + c, sum);
+              if (lane == (c & 31)) s_pool[warp * CP + c] = sum;
             }
           }
         };
@@ -939,23 +940,26 @@ resnet_tc_sweep_kernel(const SwParams p) {
         float wv[2] = {0.f, 0.f};
         if (warp < p.n_labels) fold(warp, wv);
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        for (int lb = warp; lb < p.n_labels; lb += kEpiWarps) {
-          if (lb != warp) fold(lb, wv);
-          float v = 0.f;
+        if (warp < p.n_labels) {
+          float ps[2] = {0.f, 0.f};   // this lane's channels: the epilogue warps' shares, added in warp order
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const int c = lane + 32 * k;
-            if (c < p.C) v = fmaf(s_pool[c], wv[k], v);
+            if (c < p.C)
+              for (int e = 0; e < kEpiWarps; ++e) ps[k] += s_pool[e * CP + c];
           }
+          for (int lb = warp; lb < p.n_labels; lb += kEpiWarps) {
+            if (lb != warp) fold(lb, wv);
+            float v = fmaf(ps[0], wv[0], ps[1] * wv[1]);
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) p.logits[b * p.n_labels + lb] = v + __ldg(p.out_b + lb);
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) p.logits[b * p.n_labels + lb] = v + __ldg(p.out_b + lb);
+          }
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      if (et < CP) s_pool[et] = 0.f;
-      // the next writers of s_pool (last layer of the next utterance) are at most one accumulator ring
-      // ahead of this thread, i.e. far behind this store
+      // (no second barrier: s_pool is rewritten, never accumulated into, and its next writers -- the last layer of the
+      // next utterance -- are a whole utterance minus one accumulator ring behind this read)
+      (void)et;
       if (edbg) { const long long t = clock64(); e_math += t - e_t; e_t = t; }
     }
     if (edbg && lane == 0) {

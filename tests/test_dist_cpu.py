@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from honk2_b200.dist import all_gather_rows, all_reduce_counts, shard_bounds
+from honk2_b200.dist import LogitsGather, all_gather_rows, all_reduce_counts, shard_bounds
 from oracle import model_ref
 
 
@@ -35,7 +35,15 @@ def _worker(rank, world, port, n, q):
     full = all_gather_rows(local, n)
     c, t = model_ref.acc_counts(local, target[lo:hi]) if hi > lo else (0, 0)
     counts = all_reduce_counts(torch.tensor([c, t], dtype=torch.int64))
-    q.put((rank, torch.equal(full, logits), counts.tolist(), list(model_ref.acc_counts(logits, target))))
+    # the one-collective form: logits written into the gather's send block, counts next to them
+    ok = True
+    g1 = LogitsGather(n, 12, torch.device("cpu"))
+    for rep in range(2):     # (buffers are reused from step to step; ragged shards: the last rank's block is padded)
+        g1.logits.copy_(local + rep)
+        g1.counts.copy_(torch.tensor([c + rep, t], dtype=torch.int64))
+        full1, counts1 = g1.exchange()
+        ok = ok and torch.equal(full1, logits + rep) and counts1.tolist() == [counts[0].item() + world * rep, n]
+    q.put((rank, torch.equal(full, logits) and ok, counts.tolist(), list(model_ref.acc_counts(logits, target))))
     dist.barrier()
     dist.destroy_process_group()
 
