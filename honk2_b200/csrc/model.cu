@@ -32,6 +32,7 @@ struct Model {
   float* r_out_w = nullptr;               // [L][C]
   float* r_out_b = nullptr;               // [L]
   TcResNet* tc = nullptr;                 // bf16 tensor-core plan (conv_tc.cu)
+  TcCnn* tcc = nullptr;                   // bf16 tensor-core plan of the CNN family (cnn_tc.cu)
 
   // ---- CNN packed weights
   float *c_conv0_w = nullptr, *c_conv0_b = nullptr, *c_conv1_w = nullptr, *c_conv1_b = nullptr;
@@ -337,6 +338,14 @@ extern "C" int kws_cnn_create(const kws_cnn_config* cfg, kws_model_t** out) {
       m->c_lin_w[i] = reinterpret_cast<float*>(base + o_lw[i]);
       m->c_lin_b[i] = reinterpret_cast<float*>(base + o_lb[i]);
     }
+  {
+    const int st = tc_cnn_create(c, &m->tcc);
+    if (st != KWS_OK) {
+      cudaFree(m->blob);
+      delete m;
+      return st;
+    }
+  }
   *out = m;
   return KWS_OK;
 }
@@ -371,6 +380,7 @@ extern "C" int kws_cnn_set_weights(kws_model_t* m, const kws_cnn_weights* w, voi
                              cudaMemcpyDeviceToDevice, st));
     KWS_CUDA(cudaMemcpyAsync(m->c_lin_b[i], lb[i], sizeof(float) * m->c_lin_out[i], cudaMemcpyDeviceToDevice, st));
   }
+  KWS_TRY(tc_cnn_set_weights(m->tcc, *w, st));
   m->weights_set = true;
   return KWS_OK;
 }
@@ -452,6 +462,7 @@ static int cnn_forward_f32(Model* m, const float* feat, int64_t B, int T, int F,
 extern "C" void kws_model_destroy(kws_model_t* m) {
   if (!m) return;
   if (m->tc) tc_resnet_destroy(m->tc);
+  if (m->tcc) tc_cnn_destroy(m->tcc);
   if (m->blob) cudaFree(m->blob);
   delete m;
 }
@@ -471,6 +482,7 @@ extern "C" size_t kws_model_workspace_bytes(const kws_model_t* m, int64_t B, int
     return 0;
   }
   if (precision == KWS_FP32) return cnn_ws_f32(m, B, nullptr);
+  if (precision == KWS_BF16) return tc_cnn_workspace_bytes(m->tcc, B, T, F, m->chunk[KWS_BF16]);
   return 0;
 }
 
@@ -492,11 +504,17 @@ extern "C" int kws_model_forward(kws_model_t* m, const float* feat, int64_t B, i
       st = tc_resnet_forward(m->tc, feat, B, T, F, logits, workspace, workspace_bytes, m->chunk[precision],
                              precision == KWS_BF16X3, &m->prof, as_stream(stream));
   } else {
-    if (precision != KWS_FP32) {
-      set_error("kws_model_forward: the CNN family has no tensor-core path yet");
+    const char* why = "";
+    if (precision == KWS_BF16 && tc_cnn_supported(m->tcc, &why)) {
+      st = tc_cnn_forward(m->tcc, feat, B, T, F, logits, workspace, workspace_bytes, m->chunk[KWS_BF16], &m->prof,
+                          as_stream(stream));
+    } else if (precision != KWS_FP32) {
+      set_error("kws_model_forward: this CNN configuration has no tensor-core path in precision %d (%s)", precision,
+                precision == KWS_BF16 ? why : "only bf16 is built for the CNN family");
       return KWS_ERR_UNSUPPORTED;
+    } else {
+      st = cnn_forward_f32(m, feat, B, T, F, logits, workspace, workspace_bytes, as_stream(stream));
     }
-    st = cnn_forward_f32(m, feat, B, T, F, logits, workspace, workspace_bytes, as_stream(stream));
   }
   m->prof.finish(as_stream(stream));
   m->last_launches = g_launches;
@@ -543,6 +561,8 @@ extern "C" int64_t kws_model_last_launches(const kws_model_t* m) { return m ? m-
 extern "C" const char* kws_model_kernel_path(const kws_model_t* m, int T, int F, int precision) {
   if (m == nullptr) return "unsupported";
   if (precision != KWS_BF16 && precision != KWS_BF16X3) return "fp32 CUDA-core kernels";
+  if (m->kind == KIND_CNN)
+    return precision == KWS_BF16 && tc_cnn_supported(m->tcc, nullptr) ? "cnn_tc_fused_kernel" : "unsupported";
   return m->tc != nullptr ? tc_resnet_kernel_path(m->tc, T, F, precision == KWS_BF16X3) : "unsupported";
 }
 

@@ -21,4 +21,17 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
 // "conv3x3_tc_kernel" (layer per launch) or "unsupported".
 const char* tc_resnet_kernel_path(const TcResNet* p, int T, int F, bool split);
 
+
+// ---- bf16 tensor-core path of model.CNN (cnn_tc.cu): the cnn-trad-fpool3 shape family --------------------------
+struct TcCnn;   // opaque plan: packed bf16 weights and the shared-memory geometry
+
+// Always yields a plan; tc_cnn_supported tells whether this configuration has a tensor-core path (and why not).
+int tc_cnn_create(const kws_cnn_config& cfg, TcCnn** out);
+void tc_cnn_destroy(TcCnn* p);
+bool tc_cnn_supported(const TcCnn* p, const char** why);
+int tc_cnn_set_weights(TcCnn* p, const kws_cnn_weights& w, cudaStream_t st);
+size_t tc_cnn_workspace_bytes(const TcCnn* p, int64_t B, int T, int F, int chunk);   // 0: unsupported
+int tc_cnn_forward(TcCnn* p, const float* feat, int64_t B, int T, int F, float* logits, void* ws, size_t ws_bytes,
+                   int chunk, LaunchProfiler* prof, cudaStream_t st);
+
 }  // namespace kws

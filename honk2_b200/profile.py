@@ -26,8 +26,13 @@ def conv_flops(model, T, F):
                                        if isinstance(model.layers["pool_0"].kernel_size, (list, tuple))
                                        else [model.layers["pool_0"].kernel_size] * 2)
         o = calculate_conv_output_size(s, c1.kernel_size, stride=c1.stride)
-        return (2.0 * c1.out_channels * c1.in_channels * c1.kernel_size[0] * c1.kernel_size[1] * o[0] * o[1], 1,
-                "conv_1 + bias + ReLU")
+        f1 = 2.0 * c1.out_channels * c1.in_channels * c1.kernel_size[0] * c1.kernel_size[1] * o[0] * o[1]
+        if getattr(model, "precision", "fp32") == "bf16":
+            # cnn_tc_fused_kernel: conv_0 (before pooling) and conv_1 are ONE launch
+            s0 = calculate_conv_output_size([T, F], c0.kernel_size, stride=c0.stride)
+            f0 = 2.0 * c0.out_channels * c0.kernel_size[0] * c0.kernel_size[1] * s0[0] * s0[1]
+            return f0 + f1, 1, "conv_0 + ReLU + max-pool + conv_1 + bias + ReLU in ONE launch per sub-batch"
+        return f1, 1, "conv_1 + bias + ReLU"
     return 0.0, 0, "none"
 
 

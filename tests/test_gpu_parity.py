@@ -363,8 +363,62 @@ def test_bf16_chunking_and_batch_split_invariance(dev):
     assert torch.allclose(y, y3, rtol=0, atol=2e-3 * float(y.abs().max()))
 
 
-def test_bf16_not_available_for_cnn(dev):
-    m, _ = gpu_model("cnn-trad-fpool3", "default", dev, precision="bf16")
+CNN_TC = ["cnn-trad-fpool3"]     # the CNN shapes with a tensor-core path (cnn_tc.cu)
+
+
+@pytest.mark.parametrize("name", CNN_TC)
+@pytest.mark.parametrize("variant", ["default", "hardened"])
+def test_bf16_cnn_logits_vs_reference_golden(dev, name, variant, model_golden):
+    """conv_0 + pool + conv_1 on the tensor cores (cnn_tc_fused_kernel), first Linear as a bf16 split-K GEMM."""
+    m, _ = gpu_model(name, variant, dev, precision="bf16")
+    x = torch.from_numpy(model_golden["feats"]).to(dev)
+    with torch.no_grad():
+        y = m(x).cpu().numpy()
+    ref = model_golden[f"{name}/{variant}/logits"]
+    assert np.isfinite(y).all()
+    assert logit_err(y, ref) <= BF16_TOL, (name, variant, logit_err(y, ref))
+
+
+@pytest.mark.parametrize("B", [1, 149, 700])
+def test_bf16_cnn_vs_oracle_seeded_batch(dev, B):
+    """Several utterances per persistent CTA (B > 148), a partial last wave, chunking and batch splits."""
+    name = "cnn-trad-fpool3"
+    kind, cfg = model_config(name)
+    m, sd = gpu_model(name, "hardened", dev, precision="bf16")
+    feats = torch.from_numpy(mfcc_ref.compute_mfccs_batch(synth.speechlike(min(B, 64), seed=B)))
+    feats = feats.repeat((B + feats.shape[0] - 1) // feats.shape[0], 1, 1)[:B].contiguous()
+    feats = feats + 0.01 * torch.arange(B, dtype=torch.float32).view(B, 1, 1) / max(B, 1)   # every utterance distinct
+    ref = model_ref.forward(kind, sd, cfg, feats).numpy()
+    xd = feats.to(dev)
+    with torch.no_grad():
+        y = m(xd)
+        m.chunk = {"fp32": 0, "bf16": 97}
+        y2 = m(xd)
+        y3 = torch.cat([m(xd[:B // 3]), m(xd[B // 3:])]) if B >= 3 else y
+    assert logit_err(y.cpu().numpy(), ref) <= BF16_TOL, logit_err(y.cpu().numpy(), ref)
+    assert torch.equal(y, y2), "the CNN tensor-core path is deterministic: chunking must not change a bit"
+    assert torch.equal(y, y3)
+    top2 = np.sort(ref, axis=1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > 2 * BF16_TOL * np.maximum(np.abs(ref).max(axis=1), 1e-3)
+    assert np.array_equal(y.cpu().numpy().argmax(1)[decided], ref.argmax(1)[decided])
+
+
+def test_bf16_cnn_wave_to_logits(dev):
+    m, _ = gpu_model("cnn-trad-fpool3", "hardened", dev, precision="bf16")
+    ap = AudioProcessor()
+    wd = torch.from_numpy(synth.broadband(200, seed=3)).to(dev)
+    with torch.no_grad():
+        y = m.forward_wave(wd, ap)
+        y2 = m(ap.compute_mfccs_batch(wd))
+    assert torch.equal(y, y2)
+
+
+def test_tensor_core_modes_not_available_for_other_cnns(dev):
+    """Shapes outside the cnn-trad-fpool3 family (and bf16x3 for any CNN) fail loudly: no silent fp32 fallback."""
+    m, _ = gpu_model("cnn-one-fstride4", "default", dev, precision="bf16")
+    with pytest.raises(honk2_b200.NativeError):
+        m(torch.zeros(2, 101, 40, device=dev))
+    m, _ = gpu_model("cnn-trad-fpool3", "default", dev, precision="bf16x3")
     with pytest.raises(honk2_b200.NativeError):
         m(torch.zeros(2, 101, 40, device=dev))
 
