@@ -679,6 +679,7 @@ struct TcResNet {
   bool sweep_k32 = true;       // HONK2_TC_SWEEP_K32=0: single-strip maps use the planar layout of the multi-strip maps too
   int l2_policy = 1, wait_polls = 48, sweep_max_stages = 0, sweep_min_pct = 60;
   bool sweep_discard = true;
+  bool sweep_pack = true;      // HONK2_TC_SWEEP_PACK=0: short / pooled maps stay on the position-major kernel
   // chunk pipelining: consecutive chunks run on `lanes` internal streams so that the prologue / tail of one
   // chunk's layer kernels overlaps the steady state of another's (each lane has its own activation buffers)
   int lanes = 1;
@@ -834,6 +835,7 @@ int tc_resnet_create(const kws_resnet_config& cfg, TcResNet** out) {
     p->sweep_enabled = env_int("HONK2_TC_SWEEP", 1) != 0;
     p->sweep_k32 = env_int("HONK2_TC_SWEEP_K32", 1) != 0;
     p->sweep_discard = env_int("HONK2_TC_SWEEP_DISCARD", 1) != 0;
+    p->sweep_pack = env_int("HONK2_TC_SWEEP_PACK", 1) != 0;
     p->sweep_max_stages = env_int("HONK2_TC_SWEEP_STAGES", kSwMaxStages);
     p->sweep_min_pct = env_int("HONK2_TC_SWEEP_MINPCT", 60);
     p->l2_policy = env_int("HONK2_TC_L2POLICY", 1);
@@ -1121,26 +1123,47 @@ struct TcSweepPlan {
   int c0w_off = 0, w_off[2] = {0, 0}, skip_off = 0, ring_off = 0, slot_bytes = 0, slack_bytes = 0;
   int dmax = 1, chunk_rows = 0;
   bool k32 = false, split = false;
+  // packed strips (short maps): pack_n utterances stacked in one strip of Hst rows, conv_0 (+ pool) by the pre-pass kernel
+  int pack_n = 1, pack_pitch = 0, Hst = 0, pool_off = 0;
+  bool packed = false;
 };
+
+// (PH, PW) pooling windows the pre-pass kernel of the packed-strip mode is instantiated for
+static bool tc_pack_pool_ok(int ph, int pw) { return (ph == 1 && pw == 1) || (ph == 2 && pw == 2) || (ph == 4 && pw == 3); }
 
 static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W, bool split) {
   TcSweepPlan f;
+  const int H_map = H;
+  (void)H_map;
   const kws_resnet_config& c = p->cfg;
   if (!p->sweep_enabled || c.n_layers < 1 || c.n_layers > kFusedMaxLayers || c.n_labels > 4096) return f;
   if (W < 1 || W > kSwMaxW || H < 1) return f;
   if (p->NKC > 3) return f;   // 64 maps: 640 threads leave 96 registers, the epilogue spills (position-major kernel instead)
   if ((1 + c.n_layers) * p->CP * 4 > kSwKcBytes) return f;   // per-layer epilogue constants live in shared memory
-  if (c.pool_h > 1 || c.pool_w > 1) return f;   // conv_0 runs as a tensor-core pseudo-layer on the unpooled map
-  f.n_strips = ceil_div(H, 128);
-  // the 128 lanes of an MMA are 128 rows of one column: short maps (res8 / res26 after pooling) would leave
-  // most lanes idle and stay on the position-major kernel
-  if (H * 100 < f.n_strips * 128 * p->sweep_min_pct) return f;
   int dmax = 1;
   for (int i = 1; i <= c.n_layers; ++i) {
     const int d = c.use_dilation ? (1 << ((i - 1) / 3)) : 1;
     if (d > 64) return f;   // (a staged column of 128 + 2d rows per plane would no longer leave room for three stages)
     dmax = std::max(dmax, d);
   }
+  const int ph = c.pool_h > 0 ? c.pool_h : 1, pw = c.pool_w > 0 ? c.pool_w : 1;
+  const bool pooled = ph > 1 || pw > 1;
+  // The 128 lanes of an MMA are 128 rows of one column.  Short maps (res8 / res26 after pooling, short clips) are
+  // PACKED: several utterances share a strip, stacked along the rows with dmax zero rows between them, and conv_0
+  // (+ ReLU + AvgPool) is computed by a CUDA-core pre-pass (the sweep's own conv_0 pseudo-layer works on the unpooled map).
+  const bool is_short = H * 100 < ceil_div(H, 128) * 128 * p->sweep_min_pct;
+  if (pooled || is_short) {
+    const int pitch = H + dmax;
+    const int n = (128 + dmax) / pitch;
+    if (!p->sweep_pack || n < 1 || !tc_pack_pool_ok(ph, pw) || !(p->sweep_k32 || split)) return f;
+    f.packed = true;
+    f.pack_n = n;
+    f.pack_pitch = pitch;
+    f.Hst = n * pitch - dmax;
+    if (f.Hst * 100 < 128 * p->sweep_min_pct && n == 1) return f;   // a single short map gains nothing here
+  }
+  if (f.packed) H = f.Hst;   // from here on the "map" is the stack
+  f.n_strips = ceil_div(H, 128);
   f.n_slots = p->n_sms;
   f.dmax = dmax;
   f.split = split;
@@ -1154,7 +1177,8 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W, bool split) {
   f.w_off[0] = f.c0w_off + round_up(3 * 2 * 3 * p->CP * 16, 128);
   f.w_off[1] = split ? f.w_off[0] : f.w_off[0] + round_up(w_bytes, 128);   // (split: one buffer, see the kernel)
   f.skip_off = round_up(f.w_off[1] + w_bytes, 1024);
-  f.ring_off = f.skip_off + (split ? 0 : p->NKC * p->NP * 2048);   // one skip slot per epilogue warp group
+  f.pool_off = f.skip_off + (split ? 0 : p->NKC * p->NP * 2048);   // one skip slot per epilogue warp group
+  f.ring_off = f.pool_off + (f.pack_n > 1 ? round_up(f.pack_n * 4 * p->NKC * p->CP * 4, 1024) : 0);   // packed: pooled sums per stacked utterance
   // rows per chunk of a staged column.  The split mode stages twice the chunks: its chunks are cut down to the rows
   // the map's own lanes read (H + 2 dmax); the lanes past the map then read into the next chunk / the slack.
   const int full_rows = (128 + 2 * dmax + 7) & ~7;
@@ -1169,33 +1193,177 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W, bool split) {
   return f;
 }
 
-static size_t tc_sweep_ws_bytes(const TcResNet* p, const TcSweepPlan& f, int H, int W, size_t* buf_out) {
-  const size_t buf = round_up<size_t>((size_t)f.n_slots * (f.split ? 2 : 1) * p->NP * H * W * 16, 1024);
-  if (buf_out) *buf_out = buf;
-  return 2 * buf;
+// packed strips: utterances per pre-pass + sweep launch pair (a multiple of the group size)
+static int64_t tc_pack_chunk(const TcSweepPlan& f, int64_t B, int chunk_cfg) {
+  int64_t c = chunk_cfg > 0 ? chunk_cfg : 4096;
+  c = round_up<int64_t>(c, f.pack_n);
+  return std::min<int64_t>(c, round_up<int64_t>(std::max<int64_t>(B, 1), f.pack_n));
 }
 
-template <int NKC, bool DBG, bool K32, bool SPLIT>
+static size_t tc_sweep_ws_bytes(const TcResNet* p, const TcSweepPlan& f, int H, int W, int64_t B, int chunk_cfg,
+                                size_t* buf_out, size_t* ext_group_out = nullptr) {
+  const int Hs = f.packed ? f.Hst : H;
+  const size_t buf = round_up<size_t>((size_t)f.n_slots * (f.split ? 2 : 1) * p->NP * Hs * W * 16, 1024);
+  if (buf_out) *buf_out = buf;
+  size_t ext = 0;
+  if (f.packed) {
+    const size_t per_group = (size_t)(f.split ? 2 : 1) * p->NP * Hs * W * 16;
+    if (ext_group_out) *ext_group_out = per_group;
+    ext = round_up<size_t>((size_t)(tc_pack_chunk(f, B, chunk_cfg) / f.pack_n) * per_group, 1024);
+  }
+  return 2 * buf + ext;
+}
+
+// conv_0 (1 -> C, 3x3, pad 1) + ReLU + AvgPool(PH, PW) (resnet.py:40-44) for the packed-strip mode of the sweep kernel:
+// writes the bf16 activations of a group of `pack_n` stacked utterances exactly as the sweep kernel's epilogue would
+// ([K chunk][w][stacked row][16 ch = 32 B], halves swapped where ((dmax + row) >> 2) & 1, zero rows between the
+// utterances; split: the lo parts in chunks NKC .. 2 NKC-1).  One block = one column of one group, one thread = one row.
+template <int PH, int PW>
+__global__ void __launch_bounds__(128)
+conv0_pool_pack_kernel(const float* __restrict__ feat, const float* __restrict__ w0, uint4* __restrict__ ext, int64_t B_utt,
+                       int T, int F, int C, int NKC, int W, int Hs, int pitch, int pack_n, int Hst, int dmax, int split,
+                       int64_t ext_stride) {
+  __shared__ __align__(16) float s_w[64 * 12];
+  const int CP = 16 * NKC;
+  for (int i = threadIdx.x; i < CP * 12; i += blockDim.x) {
+    const int c = i / 12, k = i - c * 12;
+    s_w[i] = (k < 9 && c < C) ? w0[c * 9 + k] : 0.f;
+  }
+  __syncthreads();
+  const int64_t g = blockIdx.x / W;
+  const int wo = blockIdx.x - (int)(g * W);
+  const int row = threadIdx.x;
+  if (row >= Hst) return;
+  const int u = row / pitch, ho = row - u * pitch;
+  const int64_t b = g * pack_n + u;
+  const bool live = ho < Hs && u < pack_n && b < B_utt;
+  float patch[PH + 2][PW + 2];
+#pragma unroll
+  for (int a = 0; a < PH + 2; ++a)
+#pragma unroll
+    for (int e = 0; e < PW + 2; ++e) {
+      const int hh = ho * PH - 1 + a, ww = wo * PW - 1 + e;
+      patch[a][e] = (live && hh >= 0 && hh < T && ww >= 0 && ww < F) ? __ldg(feat + (b * T + hh) * (int64_t)F + ww) : 0.f;
+    }
+  constexpr float inv = 1.f / (float)(PH * PW);
+  const int swl = ((dmax + row) >> 2) & 1;
+  for (int kc = 0; kc < NKC; ++kc) {
+    float out[16];
+#pragma unroll
+    for (int cl = 0; cl < 16; ++cl) {
+      const float* wc = s_w + (16 * kc + cl) * 12;
+      const float4 wa = *reinterpret_cast<const float4*>(wc);
+      const float4 wb = *reinterpret_cast<const float4*>(wc + 4);
+      const float w8 = wc[8];
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < PH; ++i)
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+          float v = patch[i][j] * wa.x;
+          v = fmaf(patch[i][j + 1], wa.y, v); v = fmaf(patch[i][j + 2], wa.z, v);
+          v = fmaf(patch[i + 1][j], wa.w, v); v = fmaf(patch[i + 1][j + 1], wb.x, v); v = fmaf(patch[i + 1][j + 2], wb.y, v);
+          v = fmaf(patch[i + 2][j], wb.z, v); v = fmaf(patch[i + 2][j + 1], wb.w, v); v = fmaf(patch[i + 2][j + 2], w8, v);
+          acc += fmaxf(v, 0.f);
+        }
+      out[cl] = live ? acc * inv : 0.f;
+    }
+    uint4 hi[2], lo[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&hi[hf]);
+      __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&lo[hf]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = out[8 * hf + 2 * e], c2 = out[8 * hf + 2 * e + 1];
+        hb[e] = __floats2bfloat162_rn(a, c2);
+        const float2 fh = __bfloat1622float2(hb[e]);
+        lb[e] = __floats2bfloat162_rn(a - fh.x, c2 - fh.y);
+      }
+    }
+    uint4* dst = ext + g * ext_stride + ((int64_t)(kc * W + wo) * Hst + row) * 2;
+    dst[swl] = hi[0];
+    dst[swl ^ 1] = hi[1];
+    if (split) {
+      uint4* dl = ext + g * ext_stride + ((int64_t)((NKC + kc) * W + wo) * Hst + row) * 2;
+      dl[swl] = lo[0];
+      dl[swl ^ 1] = lo[1];
+    }
+  }
+}
+
+static int tc_launch_conv0_pack(int ph, int pw, const float* feat, const float* w0, uint4* ext, int64_t B_utt, int64_t groups,
+                                int T, int F, int C, int NKC, int W, int Hs, const TcSweepPlan& f, int64_t ext_stride,
+                                cudaStream_t st) {
+  const int64_t blocks = groups * W;
+  KWS_REQUIRE(blocks < (int64_t)2147483647, "conv_0 pre-pass: batch too large for one launch");
+#define KWS_C0P(PH, PW)                                                                                                  \
+  conv0_pool_pack_kernel<PH, PW><<<(unsigned)blocks, 128, 0, st>>>(feat, w0, ext, B_utt, T, F, C, NKC, W, Hs, f.pack_pitch,    \
+                                                                   f.pack_n, f.Hst, f.dmax, f.split ? 1 : 0, ext_stride)
+  if (ph == 1 && pw == 1) KWS_C0P(1, 1);
+  else if (ph == 2 && pw == 2) KWS_C0P(2, 2);
+  else if (ph == 4 && pw == 3) KWS_C0P(4, 3);
+  else { set_error("conv_0 pre-pass: pooling %dx%d is not instantiated", ph, pw); return KWS_ERR_UNSUPPORTED; }
+#undef KWS_C0P
+  KWS_CHECK_LAUNCH();
+  return KWS_OK;
+}
+
+template <int NKC, bool DBG, bool K32, bool SPLIT, bool PACK>
 static int tc_launch_sweep_v(const SwParams& prm, int grid, int smem, cudaStream_t st) {
-  KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC, DBG, K32, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  resnet_tc_sweep_kernel<NKC, DBG, K32, SPLIT><<<grid, sw_threads(NKC), smem, st>>>(prm);
+  KWS_CUDA(cudaFuncSetAttribute(resnet_tc_sweep_kernel<NKC, DBG, K32, SPLIT, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  resnet_tc_sweep_kernel<NKC, DBG, K32, SPLIT, PACK><<<grid, sw_threads(NKC), smem, st>>>(prm);
   KWS_CHECK_LAUNCH();
   return KWS_OK;
 }
 
 template <int NKC>
 static int tc_launch_sweep(const SwParams& prm, bool split, int grid, int smem, cudaStream_t st) {
-  if (split) return tc_launch_sweep_v<NKC, false, true, true>(prm, grid, smem, st);
+  if (prm.ext_in != nullptr)   // packed strips (always the 32-byte-row layout; no cycle-accounting build)
+    return split ? tc_launch_sweep_v<NKC, false, true, true, true>(prm, grid, smem, st)
+                 : tc_launch_sweep_v<NKC, false, true, false, true>(prm, grid, smem, st);
+  if (split) return tc_launch_sweep_v<NKC, false, true, true, false>(prm, grid, smem, st);
   if (prm.debug != nullptr)
-    return prm.k32 ? tc_launch_sweep_v<NKC, true, true, false>(prm, grid, smem, st) : tc_launch_sweep_v<NKC, true, false, false>(prm, grid, smem, st);
-  return prm.k32 ? tc_launch_sweep_v<NKC, false, true, false>(prm, grid, smem, st) : tc_launch_sweep_v<NKC, false, false, false>(prm, grid, smem, st);
+    return prm.k32 ? tc_launch_sweep_v<NKC, true, true, false, false>(prm, grid, smem, st) : tc_launch_sweep_v<NKC, true, false, false, false>(prm, grid, smem, st);
+  return prm.k32 ? tc_launch_sweep_v<NKC, false, true, false, false>(prm, grid, smem, st) : tc_launch_sweep_v<NKC, false, false, false, false>(prm, grid, smem, st);
 }
 
+static int tc_sweep_launch(TcResNet* p, const TcSweepPlan& f, const float* feat, int64_t B, int64_t B_utt, int T, int F, int H,
+                           int W, float* logits, void* ws, size_t buf, const uint4* ext, int64_t ext_stride, int sub_h,
+                           LaunchProfiler* prof, cudaStream_t st);
+
 static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat, int64_t B, int T, int F, int H, int W,
-                            float* logits, void* ws, LaunchProfiler* prof, cudaStream_t st) {
+                            float* logits, void* ws, int chunk_cfg, LaunchProfiler* prof, cudaStream_t st) {
   const kws_resnet_config& c = p->cfg;
-  size_t buf = 0;
-  tc_sweep_ws_bytes(p, f, H, W, &buf);
+  size_t buf = 0, ext_group = 0;
+  tc_sweep_ws_bytes(p, f, H, W, B, chunk_cfg, &buf, &ext_group);
+  const int n = c.n_layers;
+  if (f.packed) {
+    // packed strips: conv_0 + pool by the pre-pass kernel, then the sweep over groups of pack_n stacked utterances,
+    // one launch pair per sub-batch.  The rows between stacked utterances are never stored: zero both buffers once.
+    KWS_CUDA(cudaMemsetAsync(ws, 0, 2 * buf, st));
+    const int64_t chunk = tc_pack_chunk(f, B, chunk_cfg);
+    const int ph = c.pool_h > 0 ? c.pool_h : 1, pw = c.pool_w > 0 ? c.pool_w : 1;
+    uint4* ext = reinterpret_cast<uint4*>(static_cast<char*>(ws) + 2 * buf);
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+      const int64_t nb = std::min(chunk, B - b0);
+      const int64_t groups = ceil_div<int64_t>(nb, f.pack_n);
+      if (prof) prof->tick(1, st);
+      KWS_TRY(tc_launch_conv0_pack(ph, pw, feat + b0 * (int64_t)T * F, p->conv0_w, ext, nb, groups, T, F, c.n_maps, p->NKC, W,
+                                   H, f, (int64_t)(ext_group / 16), st));
+      KWS_TRY(tc_sweep_launch(p, f, nullptr, groups, nb, T, F, f.Hst, W, logits + b0 * c.n_labels, ws, buf, ext,
+                              (int64_t)(ext_group / 16), H, prof, st));
+    }
+    return KWS_OK;
+  }
+  return tc_sweep_launch(p, f, feat, B, B, T, F, H, W, logits, ws, buf, nullptr, 0, H, prof, st);
+}
+
+// one launch of the sweep kernel: B units (utterances, or groups of stacked utterances when ext != nullptr)
+static int tc_sweep_launch(TcResNet* p, const TcSweepPlan& f, const float* feat, int64_t B, int64_t B_utt, int T, int F, int H,
+                           int W, float* logits, void* ws, size_t buf, const uint4* ext, int64_t ext_stride, int sub_h,
+                           LaunchProfiler* prof, cudaStream_t st) {
+  const kws_resnet_config& c = p->cfg;
   const int n = c.n_layers;
   // (no device-side tables: every per-layer quantity is derived from these parameters inside the kernel, so a change
   // of batch size, shape or workspace costs nothing)
@@ -1218,7 +1386,11 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
   prm.chunk_rows = f.chunk_rows;
   prm.ring_slack_bytes = f.slack_bytes;
   prm.k32 = f.k32 ? 1 : 0;
-  prm.discard_q = p->sweep_discard && f.n_strips == 1 && !f.split;
+  prm.discard_q = p->sweep_discard && f.n_strips == 1 && !f.split && !f.packed;   // (packed: the zero rows inside a column must survive)
+  prm.ext_in = ext; prm.ext_stride = ext_stride;
+  prm.pack_n = f.packed ? f.pack_n : 1; prm.pack_h = sub_h; prm.pack_pitch = f.packed ? f.pack_pitch : H;
+  prm.smem_pool_off = f.pool_off;
+  prm.B_utt = B_utt;
   prm.smem_w_off[0] = f.w_off[0]; prm.smem_w_off[1] = f.w_off[1];
   prm.smem_ring_off = f.ring_off; prm.ring_slot_bytes = f.slot_bytes; prm.n_stages = f.n_stages;
   prm.l2_policy = p->l2_policy;
@@ -1230,7 +1402,7 @@ static int tc_sweep_forward(TcResNet* p, const TcSweepPlan& f, const float* feat
   const int grid = (int)std::min<int64_t>(f.n_slots, B);
   static const bool dbg_on = [] { const char* e = std::getenv("HONK2_TC_DEBUG"); return e && std::atoi(e) != 0; }();
   static long long* dbg_buf = nullptr;
-  if (dbg_on && !f.split) {
+  if (dbg_on && !f.split && !f.packed) {
     if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(long long));
     prm.debug = dbg_buf;
     const char* e = std::getenv("HONK2_TC_DIAG");
@@ -1296,14 +1468,14 @@ size_t tc_resnet_workspace_bytes(const TcResNet* p, int64_t B, int T, int F, int
   const TcSweepPlan sp = tc_sweep_plan(p, H, W, split);
   const TcFusedPlan f = tc_fused_plan(p, H, W, split);
   if (split) {   // the split-bf16 mode exists in the two whole-network kernels only
-    if (sp.ok) return tc_sweep_ws_bytes(p, sp, H, W, nullptr);
+    if (sp.ok) return tc_sweep_ws_bytes(p, sp, H, W, B, chunk, nullptr);
     return f.ok ? tc_fused_ws_bytes(p, f, W, nullptr) : 0;
   }
   const int64_t c = tc_chunk(p, B, H, W, chunk);
   const size_t layered = p->lanes * tc_lane_bytes(p, c, H, W, nullptr);
   // the layer-per-launch path stays available (profiling, shapes the fused kernel cannot stage)
   size_t need = f.ok ? std::max(layered, tc_fused_ws_bytes(p, f, W, nullptr)) : layered;
-  if (sp.ok) need = std::max(need, tc_sweep_ws_bytes(p, sp, H, W, nullptr));
+  if (sp.ok) need = std::max(need, tc_sweep_ws_bytes(p, sp, H, W, B, chunk, nullptr));
   return need;
 }
 
@@ -1372,7 +1544,7 @@ int tc_resnet_forward(TcResNet* p, const float* feat, int64_t B, int T, int F, f
     const bool layered = prof && prof->enabled && prof_layered && !split;
     const TcSweepPlan sp = tc_sweep_plan(p, H, W, split);
     if (sp.ok && !layered) {
-      return tc_sweep_forward(p, sp, feat, B, T, F, H, W, logits, ws, prof, st);
+      return tc_sweep_forward(p, sp, feat, B, T, F, H, W, logits, ws, chunk_cfg, prof, st);
     }
     const TcFusedPlan f = tc_fused_plan(p, H, W, split);
     if (f.ok && !layered) {

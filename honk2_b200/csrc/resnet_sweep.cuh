@@ -122,11 +122,22 @@ struct SwParams {
   int diag;                     // diagnostics (wrong results!): 1 = epilogue skips math and stores, 2 = skips the skip-tensor loads
   long long* debug;             // optional cycle counters of CTA 0 (HONK2_TC_DEBUG=1)
   long long* trace;             // optional [8][kSwTraceLen] event timestamps of CTA 0 (HONK2_TC_TRACE=1, needs DEBUG)
+  // Packed strips (short maps: res8 / res26 after pooling, short clips): `pack_n` utterances share ONE strip, stacked along
+  // the rows with `pack_pitch - pack_h` >= dmax zero rows between them (never stored: they are the zero padding of both
+  // neighbours).  H is then the stacked height, B counts GROUPS of pack_n utterances, and conv_0 (+ ReLU + AvgPool,
+  // resnet.py:40-44) has been computed by conv0_pool_pack_kernel into `ext_in`, which the first layer reads instead of P
+  // and the second layer adds as its skip tensor.
+  const uint4* ext_in;          // [groups][NA chunks][W][H][32 B] (nullptr: conv_0 runs in this kernel as a pseudo-layer)
+  int64_t ext_stride;           // 16-byte units per group
+  int pack_n, pack_h, pack_pitch;
+  int smem_pool_off;            // pack_n > 1: [pack_n][epilogue warps][CP] f32 pooled sums
+  int64_t B_utt;                // utterances (packed mode: the last group may be partly empty)
 };
 
-template <int NKC, bool DBG, bool K32, bool SPLIT>
+template <int NKC, bool DBG, bool K32, bool SPLIT, bool PACK>
 __global__ void __launch_bounds__(sw_threads(NKC), 1)
 resnet_tc_sweep_kernel(const SwParams p) {
+  static_assert(K32 || !PACK, "packed strips are built on the 32-byte-row layout");
   static_assert(K32 || !SPLIT, "the split-bf16 mode is built on the 32-byte-row layout");
   constexpr int NA = SPLIT ? 2 * NKC : NKC;            // activation chunks staged per column (SPLIT: hi chunks, then lo chunks)
   constexpr int kEpiWarps = sw_epi_warps(NKC);
@@ -153,7 +164,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
   constexpr uint32_t SKIP_SLOT = NP * 128 * 16;   // bytes
   auto col_bar = [&](int par, int w) { return sbase + kSwBarCol + 8u * (par * kSwMaxW + w); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSwTmemSlot);
-  float* s_pool = reinterpret_cast<float*>(smem + kSwPool);
+  float* s_pool = reinterpret_cast<float*>(smem + (PACK ? p.smem_pool_off : kSwPool));
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -162,6 +173,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
   const int64_t n_wq = n_my * n_layers;        // real (C -> C) layers this CTA runs
   const int64_t n_seq = n_wq;
   const int nl1 = n_layers + 1;                 // pseudo-layers per utterance: conv_0, then the C -> C layers
+  constexpr bool ext = PACK;                    // conv_0 came from conv0_pool_pack_kernel: no conv_0 pseudo-layer here
+  constexpr int ll0 = ext ? 1 : 0;
 
   // Activation layout in HBM (16-byte units = 8 bf16 channels of one position), one slot per CTA:
   //   k32     [K chunk][w][h][2]      (single-strip maps; SPLIT: 2 NKC chunks, the lo parts after the hi parts)
@@ -256,8 +269,9 @@ resnet_tc_sweep_kernel(const SwParams p) {
       }
       for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
         const float* feat_b = p.feat + b * (int64_t)p.T * p.F;
+        const uint4* ext_b = ext ? p.ext_in + b * p.ext_stride : nullptr;
         const bool c0_vec = (p.F & 3) == 0 && (reinterpret_cast<uintptr_t>(p.feat) & 15) == 0;
-        for (int ll = 0; ll < nl1; ++ll, ++sq) {
+        for (int ll = ll0; ll < nl1; ++ll, ++sq) {
           const bool is_c0 = ll == 0;
           const int l = ll - 1;
           const int d = is_c0 ? 1 : layer_dil(l);
@@ -274,7 +288,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
             } else if (wq >= 1) {
               // buffer (wq+1)&1 was read by the MMAs of the previous real layer: wait until they have retired
               // (that layer is the previous pseudo-layer, or the one before conv_0 when this is the utterance's first)
-              const int64_t sp = l >= 1 ? sq - 1 : sq - 2;
+              const int64_t sp = (l >= 1 || ext) ? sq - 1 : sq - 2;
               mbar_wait(layer_bar((int)(sp & 1)), (uint32_t)((sp >> 1) & 1));
             }
             const int nl = (l + 1 < n_layers) ? l + 1 : 0;
@@ -376,7 +390,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
               for (int w = r; w < W; w += d, ++step) {
                 if (!SPLIT && w_pending && step == kSwWeightStep) request_weights();
                 pstamp(pd_issue);
-                if (!is_c0) wait_lean(col_bar(prev_par, w), prev_phase);   // column w of the previous pseudo-layer is stored
+                if (!is_c0 && !(ext && l == 0)) wait_lean(col_bar(prev_par, w), prev_phase);   // column w of the previous pseudo-layer is stored
                 pstamp(pd_col);
                 wait_lean(empty_bar(stage), sphase ^ 1);
                 pstamp(pd_empty);
@@ -386,7 +400,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                   if (leader) {
                     const uint32_t bytes = (uint32_t)H * 32u;
                     mbar_expect_tx(full_bar(stage), bytes * NA);
-                    const uint4* src = (in_q ? bufQ : bufP) + (int64_t)w * H * 2;
+                    const uint4* src = ((ext && l == 0) ? ext_b : in_q ? bufQ : bufP) + (int64_t)w * H * 2;
                     const uint32_t d0 = dst + (uint32_t)p.dmax * 32u;
 #pragma unroll
                     for (int kc = 0; kc < NA; ++kc)
@@ -489,7 +503,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
       };
       int64_t sq = 0, wq = 0;   // pseudo-layer / real-layer counters (see the producer)
       for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
-        for (int ll = 0; ll < nl1; ++ll, ++sq) {
+        for (int ll = ll0; ll < nl1; ++ll, ++sq) {
           const bool is_c0 = ll == 0;
           const int l = ll - 1;
           const int d = is_c0 ? 1 : layer_dil(l);
@@ -650,15 +664,19 @@ resnet_tc_sweep_kernel(const SwParams p) {
     int eown = 0;        // which group owns it
     uint32_t eskpar = 0; // parity of this group's skip slot (one use per own block of a skip layer)
     int64_t sq = 0;      // pseudo-layer counter (see the producer)
+    // packed strips: the rows between two stacked utterances are never stored (they stay zero = both neighbours' padding)
+    const bool row_ok = !PACK || ((q * 32 + lane) % p.pack_pitch) < p.pack_h;
     // cycle accounting of epilogue warp 0 of CTA 0 (HONK2_TC_DEBUG=1)
     const bool edbg = DBG && p.debug != nullptr && blockIdx.x == 0 && warp == 0;
     const bool etrace = DBG && p.trace != nullptr && blockIdx.x == 0 && (warp == 0 || warp == 7) && lane == 0;
     int gblk = 0;
     long long e_wait = 0, e_tmem = 0, e_pub = 0, e_math = 0, e_conv0 = 0, e_t = clock64();
     for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
-      for (int ll = 0; ll < nl1; ++ll, ++sq) {
+      for (int ll = ll0; ll < nl1; ++ll, ++sq) {
         const bool is_c0 = ll == 0;      // conv_0 + ReLU -> P (resnet.py:40-41): no skip, no constant
         const int l = ll - 1;
+        // the skip tensor of the first skip layer is conv_0's output (resnet.py:44,52): P, or the packed pre-pass buffer
+        const uint4* skipP = (ext && l == 1) ? p.ext_in + b * p.ext_stride : bufP;
         const int64_t seq = sq;
         const int d = is_c0 ? 1 : layer_dil(l);
         const int n_runs = d < W ? d : W;
@@ -703,7 +721,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
               if (mine) {
                 const int row = it.s * 128 + q * 32 + lane;
                 ob.exists = true; ob.w = it.w; ob.s = it.s; ob.slot = esl; ob.par = epr;
-                ob.off = row >= H ? -1 : k32 ? (it.w * H + row) * 2 : it.w * H + row;
+                ob.off = (row >= H || !row_ok) ? -1 : k32 ? (it.w * H + row) * 2 : it.w * H + row;
               }
               // step the iterator, the ring slot and the owner
               ++it.o; it.w += d;
@@ -775,8 +793,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
               uint4 skv[4] = {};
               if constexpr (SPLIT && HAS_SKIP) {
                 if (valid) {
-                  const uint4* s_hi = bufP + jj * kc_stride + ob.off;
-                  const uint4* s_lo = bufP + (NKC + jj) * kc_stride + ob.off;
+                  const uint4* s_hi = skipP + jj * kc_stride + ob.off;
+                  const uint4* s_lo = skipP + (NKC + jj) * kc_stride + ob.off;
                   skv[0] = ld_cg(s_hi); skv[1] = ld_cg(s_hi + 1); skv[2] = ld_cg(s_lo); skv[3] = ld_cg(s_lo + 1);
                 }
               }
@@ -878,7 +896,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 if (q == 0 && ob.exists && elect_one()) {   // [K chunk][128 rows][32 B]
                   const uint32_t bytes = (uint32_t)H * 32u;
                   mbar_expect_tx(skfull_bar(g), bytes * NKC);
-                  const uint4* src = bufP + (int64_t)ob.w * H * 2;
+                  const uint4* src = skipP + (int64_t)ob.w * H * 2;
                   const uint32_t d0 = sbase + p.smem_skip_off + (uint32_t)g * SKIP_SLOT;
 #pragma unroll
                   for (int kc = 0; kc < NKC; ++kc)
@@ -907,12 +925,27 @@ resnet_tc_sweep_kernel(const SwParams p) {
             // fused global mean (resnet.py:57-58): warp-reduce the 32 rows; every warp leaves ITS share of every channel
             // in its own row of s_pool (no atomics: the logits below add the rows in a fixed order, so repeated
             // launches agree bit for bit)
+            if constexpr (!PACK) {
 #pragma unroll
-            for (int c = 0; c < CP; ++c) {
-              float sum = psum[c];
+              for (int c = 0; c < CP; ++c) {
+                float sum = psum[c];
 #pragma unroll
-              for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-              if (lane == (c & 31)) s_pool[warp * CP + c] = sum;
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == (c & 31)) s_pool[warp * CP + c] = sum;
+              }
+            } else {
+              // packed strips: one sum per stacked utterance (this lane's row belongs to utterance `mine`, or to none)
+              const int prow = q * 32 + lane;
+              const int mine = (row_ok && prow < H) ? prow / p.pack_pitch : -1;
+              for (int u = 0; u < p.pack_n; ++u) {
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                  float sum = mine == u ? psum[c] : 0.f;
+#pragma unroll
+                  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                  if (lane == (c & 31)) s_pool[(u * kEpiWarps + warp) * CP + c] = sum;
+                }
+              }
             }
           }
         };
@@ -929,7 +962,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
       // per utterance, ~8 000 with this form.  Under the power cap the end-to-end gain is within noise.)
       // s_pool holds sums of z = x - mean; the BatchNorm output mean is z_mean / sigma (resnet.py:55-58)
       {
-        const float inv = 1.f / (float)(H * W);
+        const int sub_h = PACK ? p.pack_h : H;
+        const float inv = 1.f / (float)(sub_h * W);
         auto fold = [&](int lb, float (&wv)[2]) {
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -941,19 +975,25 @@ resnet_tc_sweep_kernel(const SwParams p) {
         if (warp < p.n_labels) fold(warp, wv);
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (warp < p.n_labels) {
-          float ps[2] = {0.f, 0.f};   // this lane's channels: the epilogue warps' shares, added in warp order
+          const int n_sub = PACK ? p.pack_n : 1;
+          for (int u = 0; u < n_sub; ++u) {
+            const int64_t bu = PACK ? b * p.pack_n + u : b;
+            if (PACK && bu >= p.B_utt) break;
+            const float* sp = s_pool + u * kEpiWarps * CP;
+            float ps[2] = {0.f, 0.f};   // this lane's channels: the epilogue warps' shares, added in warp order
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int c = lane + 32 * k;
-            if (c < p.C)
-              for (int e = 0; e < kEpiWarps; ++e) ps[k] += s_pool[e * CP + c];
-          }
-          for (int lb = warp; lb < p.n_labels; lb += kEpiWarps) {
-            if (lb != warp) fold(lb, wv);
-            float v = fmaf(ps[0], wv[0], ps[1] * wv[1]);
+            for (int k = 0; k < 2; ++k) {
+              const int c = lane + 32 * k;
+              if (c < p.C)
+                for (int e = 0; e < kEpiWarps; ++e) ps[k] += sp[e * CP + c];
+            }
+            for (int lb = warp; lb < p.n_labels; lb += kEpiWarps) {
+              if (lb != warp || u > 0) fold(lb, wv);
+              float v = fmaf(ps[0], wv[0], ps[1] * wv[1]);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) p.logits[b * p.n_labels + lb] = v + __ldg(p.out_b + lb);
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              if (lane == 0) p.logits[bu * p.n_labels + lb] = v + __ldg(p.out_b + lb);
+            }
           }
         }
       }

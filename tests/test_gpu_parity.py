@@ -674,3 +674,69 @@ def test_eval_statistics_on_device(dev):
                    {"acc": Acc(), "per_class": PerClassAcc()}, {i: f"label{i}" for i in range(12)})
     assert set(res) == {"loss", "metric_acc", "metric_per_class"} and np.isfinite(res["loss"])
     assert all(k.startswith("label") for k in res["metric_per_class"])
+
+
+# ---------------------------------------------------------------------------------------------
+# packed strips: short maps (res8 / res26 after pooling, short clips) run on the column-sweep kernel with several
+# utterances stacked in one 128-row strip; conv_0 + ReLU + AvgPool comes from conv0_pool_pack_kernel
+
+def _kernel_path(m, dev, T=101, F=40):
+    import ctypes as C
+    lib, st = m._state(dev)
+    lib.kws_model_kernel_path.restype = C.c_char_p
+    return lib.kws_model_kernel_path(st["handle"], T, F, m._precision_id()).decode()
+
+
+@pytest.mark.parametrize("name", ["res8", "res26", "res8_narrow", "res26_narrow"])
+@pytest.mark.parametrize("precision,tol", [("bf16", BF16_TOL), ("bf16x3", LOGIT_TOL)])
+def test_packed_strips_ragged_batches_vs_oracle(dev, name, precision, tol):
+    """Batch sizes that do not fill the last group of stacked utterances, more groups than SMs, and sub-batching."""
+    kind, cfg = model_config(name)
+    m, sd = gpu_model(name, "hardened", dev, precision=precision)
+    assert _kernel_path(m, dev) == "resnet_tc_sweep_kernel"
+    base = torch.from_numpy(mfcc_ref.compute_mfccs_batch(synth.speechlike(48, seed=5)))
+    for B in (1, 5, 48, 1301):
+        feats = base.repeat((B + 47) // 48, 1, 1)[:B].contiguous()
+        feats = feats + 0.02 * torch.arange(B, dtype=torch.float32).view(B, 1, 1) / B   # every utterance distinct
+        with torch.no_grad():
+            y = m(feats.to(dev)).cpu().numpy()
+        idx = np.unique(np.concatenate([np.arange(min(B, 6)), np.arange(max(B - 6, 0), B)]))
+        ref = model_ref.forward(kind, sd, cfg, feats[idx]).numpy()
+        assert np.isfinite(y).all()
+        assert logit_err(y[idx], ref) <= tol, (name, precision, B, logit_err(y[idx], ref))
+        if precision == "bf16x3":
+            assert np.array_equal(y[idx].argmax(1), ref.argmax(1))
+    with torch.no_grad():
+        xd = feats.to(dev)
+        y_all = m(xd)
+        m.chunk = {"fp32": 0, "bf16": 250, "bf16x3": 250}
+        y_chunked = m(xd)
+    assert torch.equal(y_all, y_chunked), "stacking is per group: sub-batching must not change a bit"
+
+
+@pytest.mark.parametrize("name", ["res8", "res26"])
+def test_packed_strips_match_position_major_kernel(dev, monkeypatch, name):
+    feats = torch.from_numpy(mfcc_ref.compute_mfccs_batch(synth.broadband(300, seed=13))).to(dev)
+    with torch.no_grad():
+        m_pack, _ = gpu_model(name, "hardened", dev, precision="bf16")
+        y_pack = m_pack(feats)
+        assert _kernel_path(m_pack, dev) == "resnet_tc_sweep_kernel"
+        monkeypatch.setenv("HONK2_TC_SWEEP_PACK", "0")
+        m_pos, _ = gpu_model(name, "hardened", dev, precision="bf16")
+        y_pos = m_pos(feats)
+        assert _kernel_path(m_pos, dev) == "resnet_tc_fused_kernel"
+    assert float((y_pack - y_pos).abs().max()) <= 1e-2 * float(y_pos.abs().max())
+
+
+@pytest.mark.parametrize("name,T", [("res15", 50), ("res15", 33), ("res15_narrow", 61), ("res8", 57)])
+def test_packed_strips_short_clips(dev, name, T):
+    """Short clips: unpooled maps of fewer than 77 rows are stacked with dmax (16 for res15) zero rows between them."""
+    kind, cfg = model_config(name)
+    rng = np.random.default_rng(T)
+    feats = torch.from_numpy((rng.standard_normal((37, T, 40)) * 4 - 6).astype(np.float32))
+    for precision, tol in (("bf16", BF16_TOL), ("bf16x3", LOGIT_TOL)):
+        m, sd = gpu_model(name, "hardened", dev, precision=precision)
+        with torch.no_grad():
+            y = m(feats.to(dev)).cpu().numpy()
+        ref = model_ref.forward(kind, sd, cfg, feats).numpy()
+        assert logit_err(y, ref) <= tol, (name, T, precision, logit_err(y, ref))
