@@ -1217,7 +1217,8 @@ static size_t tc_sweep_ws_bytes(const TcResNet* p, const TcSweepPlan& f, int H, 
 // conv_0 (1 -> C, 3x3, pad 1) + ReLU + AvgPool(PH, PW) (resnet.py:40-44) for the packed-strip mode of the sweep kernel:
 // writes the bf16 activations of a group of `pack_n` stacked utterances exactly as the sweep kernel's epilogue would
 // ([K chunk][w][stacked row][16 ch = 32 B], halves swapped where ((dmax + row) >> 2) & 1, zero rows between the
-// utterances; split: the lo parts in chunks NKC .. 2 NKC-1).  One block = one column of one group, one thread = one row.
+// utterances; split: the lo parts in chunks NKC .. 2 NKC-1).  One thread = one (column, stacked row) position of a group;
+// a group's W * Hst positions are dealt to blocks of 128 threads column by column (rows fastest: 32-byte stores coalesce).
 template <int PH, int PW>
 __global__ void __launch_bounds__(128)
 conv0_pool_pack_kernel(const float* __restrict__ feat, const float* __restrict__ w0, uint4* __restrict__ ext, int64_t B_utt,
@@ -1230,10 +1231,11 @@ conv0_pool_pack_kernel(const float* __restrict__ feat, const float* __restrict__
     s_w[i] = (k < 9 && c < C) ? w0[c * 9 + k] : 0.f;
   }
   __syncthreads();
-  const int64_t g = blockIdx.x / W;
-  const int wo = blockIdx.x - (int)(g * W);
-  const int row = threadIdx.x;
-  if (row >= Hst) return;
+  const int tiles = (W * Hst + 127) >> 7;
+  const int64_t g = blockIdx.x / tiles;
+  const int item = (blockIdx.x - (int)(g * tiles)) * 128 + threadIdx.x;
+  if (item >= W * Hst) return;
+  const int wo = item / Hst, row = item - wo * Hst;
   const int u = row / pitch, ho = row - u * pitch;
   const int64_t b = g * pack_n + u;
   const bool live = ho < Hs && u < pack_n && b < B_utt;
@@ -1295,7 +1297,7 @@ conv0_pool_pack_kernel(const float* __restrict__ feat, const float* __restrict__
 static int tc_launch_conv0_pack(int ph, int pw, const float* feat, const float* w0, uint4* ext, int64_t B_utt, int64_t groups,
                                 int T, int F, int C, int NKC, int W, int Hs, const TcSweepPlan& f, int64_t ext_stride,
                                 cudaStream_t st) {
-  const int64_t blocks = groups * W;
+  const int64_t blocks = groups * ceil_div(W * f.Hst, 128);
   KWS_REQUIRE(blocks < (int64_t)2147483647, "conv_0 pre-pass: batch too large for one launch");
 #define KWS_C0P(PH, PW)                                                                                                  \
   conv0_pool_pack_kernel<PH, PW><<<(unsigned)blocks, 128, 0, st>>>(feat, w0, ext, B_utt, T, F, C, NKC, W, Hs, f.pack_pitch,    \
