@@ -455,6 +455,15 @@ def main():
         gbs = fe_bytes / (prof["frontend_ms"] / K / 1e3) / 1e9
         fe_roof = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                    "kernel": "mfcc_kernel", "ms_per_launch": prof["frontend_ms"] / K}
+        # what actually limits it (committed `ncu --set full` record of the same kernel): the SM, not HBM
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", "r2_mfcc_ncu.json")))
+            fe_roof["limiter"] = {"lsu_wavefronts_pct_of_peak": rec.get("lsu_wavefronts_pct_of_peak"),
+                                  "issue_slots_busy_pct": rec.get("issue_slots_busy_pct"),
+                                  "dram_gb_per_s": rec.get("dram_gb_per_s_under_ncu"), "source": rec.get("source"),
+                                  "note": "instruction / shared-memory bound (240-point FFT in registers + one exchange per frame)"}
+        except Exception:
+            pass
 
     dtype = {"bf16": "bf16", "bf16x3": "bf16 (split hi+lo pairs, 3 MMAs per product, fp32 accumulate)", "fp32": "f32"}[precision]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

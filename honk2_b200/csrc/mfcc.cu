@@ -159,14 +159,40 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
       s_wave[i] = b + wi < B ? __ldg(w + (int64_t)wi * wav_stride + j) : 0.f;
     }
   } else {
-    // stage: samples [160*t0 - 240, +2880) with librosa 'reflect' padding at the clip edges
+    // stage: samples [160*t0 - 240, +2880) with librosa 'reflect' padding at the clip edges; only the frames that exist
+    // (the last tile of a clip usually holds fewer than 16).  Interior runs are copied 16 bytes at a time.
     const int j0 = t0 * kHop - kNfft / 2;
-    for (int i = tid; i < kStageSamples; i += kMfccThreads) {
-      int j = j0 + i;
-      if (j < 0) j = -j;
-      if (j >= N) j = 2 * (N - 1) - j;
-      j = max(0, min(j, N - 1));  // only reachable for samples of masked frames
-      s_wave[i] = __ldg(w + j);
+    const int n_fr = min(kFramesPerCta, T - t0);
+    const int n_stage = (n_fr - 1) * kHop + kNfft;
+    const bool vec = ((reinterpret_cast<uintptr_t>(w) & 15) == 0);   // (j0 is a multiple of 16 samples)
+    if (vec) {
+      for (int i4 = tid; i4 < (n_stage >> 2); i4 += kMfccThreads) {
+        const int i = i4 << 2, j = j0 + i;
+        float4 v;
+        if (j >= 0 && j + 3 < N) {
+          v = __ldg(reinterpret_cast<const float4*>(w + j));
+        } else {
+          float e[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            int jj = j + q;
+            if (jj < 0) jj = -jj;
+            if (jj >= N) jj = 2 * (N - 1) - jj;
+            jj = max(0, min(jj, N - 1));  // only reachable for samples of masked frames
+            e[q] = __ldg(w + jj);
+          }
+          v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        *reinterpret_cast<float4*>(s_wave + i) = v;
+      }
+    } else {
+      for (int i = tid; i < n_stage; i += kMfccThreads) {
+        int j = j0 + i;
+        if (j < 0) j = -j;
+        if (j >= N) j = 2 * (N - 1) - j;
+        j = max(0, min(j, N - 1));
+        s_wave[i] = __ldg(w + j);
+      }
     }
   }
   for (int i = tid; i < kNfft; i += kMfccThreads) s_win[i] = tb.window[i];
@@ -182,6 +208,8 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
   const int t_local = 2 * warp + half;
   const int t = EDGES ? ((t_local & 3) < 2 ? (t_local & 3) : T - 4 + (t_local & 3)) : t0 + t_local;
   const int64_t b_out = EDGES ? b + (t_local >> 2) : b;
+  // (whole warps without a frame -- the tail of a clip's last tile -- are done: only __syncwarp from here on)
+  if (!EDGES && t0 + 2 * warp >= T) return;
   float2* sc = scratch + t_local * kNz;
   const float* fr = s_wave + (EDGES ? kNfft : kHop) * t_local;
 
