@@ -21,6 +21,9 @@ namespace kws {
 constexpr int kNfft = 480;
 constexpr int kHop = 160;
 constexpr int kNz = 240;            // complex FFT length
+constexpr int kScStride = kNz + 8;   // per-frame scratch pitch (float2): 496 words = 16 banks off, so the two half-warps (two
+                                     // frames) of a warp hit disjoint bank halves in the 32-bit phases (power / mel)
+constexpr int kTwA = 16 * 16;        // stage-A twiddles, [k1][lane] (lane-contiguous: no bank conflicts)
 constexpr int kFramesPerCta = 16;
 constexpr int kMfccThreads = 256;
 constexpr int kStageSamples = (kFramesPerCta - 1) * kHop + kNfft;  // 2880
@@ -29,7 +32,7 @@ constexpr int kMaxMels = 64;
 
 struct FrontendTables {
   const float* window;    // [480]
-  const float2* tw240;    // [240] (cos, -sin)(2 pi j / 240)
+  const float2* tw240;    // [16][16] stage-A twiddles W240^(l k1) = (cos, -sin)(2 pi l k1 / 240) at [k1 * 16 + l]
   const float2* tw480;    // [240] (sin, cos)(2 pi k / 480)
   const int* mel_lo;      // [n_mels] first bin
   const int* mel_cnt;     // [n_mels] number of bins
@@ -131,9 +134,9 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
             int tiles_per_utt, float* __restrict__ feat) {
   constexpr int kStage = EDGES ? kEdgeStageSamples : kStageSamples;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* scratch = reinterpret_cast<float2*>(smem_raw);                 // [16][240]
-  float2* s_tw240 = scratch + kFramesPerCta * kNz;                       // [240]
-  float2* s_tw480 = s_tw240 + kNz;                                       // [240]
+  float2* scratch = reinterpret_cast<float2*>(smem_raw);                 // [16][248]
+  float2* s_tw240 = scratch + kFramesPerCta * kScStride;                 // [16][16]
+  float2* s_tw480 = s_tw240 + kTwA;                                      // [240]
   float* s_wave = reinterpret_cast<float*>(s_tw480 + kNz);               // [2880] ([16][480] for EDGES)
   float* s_win = s_wave + kStage;                                        // [480]
   int* s_lo = reinterpret_cast<int*>(s_win + kNfft);                     // [64]
@@ -196,7 +199,8 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
     }
   }
   for (int i = tid; i < kNfft; i += kMfccThreads) s_win[i] = tb.window[i];
-  for (int i = tid; i < kNz; i += kMfccThreads) { s_tw240[i] = tb.tw240[i]; s_tw480[i] = tb.tw480[i]; }
+  for (int i = tid; i < kNz; i += kMfccThreads) s_tw480[i] = tb.tw480[i];
+  for (int i = tid; i < kTwA; i += kMfccThreads) s_tw240[i] = tb.tw240[i];
   for (int i = tid; i < tb.n_mels; i += kMfccThreads) {
     s_lo[i] = tb.mel_lo[i]; s_cnt[i] = tb.mel_cnt[i]; s_off[i] = tb.mel_off[i];
   }
@@ -210,7 +214,7 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
   const int64_t b_out = EDGES ? b + (t_local >> 2) : b;
   // (whole warps without a frame -- the tail of a clip's last tile -- are done: only __syncwarp from here on)
   if (!EDGES && t0 + 2 * warp >= T) return;
-  float2* sc = scratch + t_local * kNz;
+  float2* sc = scratch + t_local * kScStride;
   const float* fr = s_wave + (EDGES ? kNfft : kHop) * t_local;
 
   // ---- stage A: 15 radix-16 FFTs over n1 (lane = n2), twiddle by W240^(n2 k1)
@@ -227,7 +231,7 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int k1 = bitrev4(i);
-      sc[k1 * 15 + l] = cmul(x[i], s_tw240[l * k1]);
+      sc[k1 * 15 + l] = cmul(x[i], s_tw240[k1 * 16 + l]);
     }
   }
   __syncwarp();
@@ -359,21 +363,24 @@ extern "C" int kws_frontend_create(int sr, int n_mels, float f_min, float f_max,
   const double PI = 3.14159265358979323846;
   std::vector<float> window(kNfft);
   for (int n = 0; n < kNfft; ++n) window[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfft));
-  std::vector<float2> tw240(kNz), tw480(kNz);
-  for (int j = 0; j < kNz; ++j) {
-    tw240[j] = make_float2((float)std::cos(2.0 * PI * j / kNz), (float)(-std::sin(2.0 * PI * j / kNz)));
+  std::vector<float2> tw240(kTwA), tw480(kNz);
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int l = 0; l < 16; ++l) {
+      const int j = (l * k1) % kNz;
+      tw240[k1 * 16 + l] = make_float2((float)std::cos(2.0 * PI * j / kNz), (float)(-std::sin(2.0 * PI * j / kNz)));
+    }
+  for (int j = 0; j < kNz; ++j)
     tw480[j] = make_float2((float)std::sin(2.0 * PI * j / kNfft), (float)std::cos(2.0 * PI * j / kNfft));
-  }
 
   // one device blob
   const size_t nnz = wts.size();
-  size_t o_win = 0, o_tw240 = o_win + sizeof(float) * kNfft, o_tw480 = o_tw240 + sizeof(float2) * kNz,
+  size_t o_win = 0, o_tw240 = o_win + sizeof(float) * kNfft, o_tw480 = o_tw240 + sizeof(float2) * kTwA,
          o_lo = o_tw480 + sizeof(float2) * kNz, o_cnt = o_lo + sizeof(int) * n_mels,
          o_off = o_cnt + sizeof(int) * n_mels, o_w = o_off + sizeof(int) * n_mels,
          total = o_w + sizeof(float) * (nnz + 1);
   std::vector<unsigned char> host(total);
   memcpy(host.data() + o_win, window.data(), sizeof(float) * kNfft);
-  memcpy(host.data() + o_tw240, tw240.data(), sizeof(float2) * kNz);
+  memcpy(host.data() + o_tw240, tw240.data(), sizeof(float2) * kTwA);
   memcpy(host.data() + o_tw480, tw480.data(), sizeof(float2) * kNz);
   memcpy(host.data() + o_lo, lo.data(), sizeof(int) * n_mels);
   memcpy(host.data() + o_cnt, cnt.data(), sizeof(int) * n_mels);
@@ -399,7 +406,7 @@ extern "C" int kws_frontend_create(int sr, int n_mels, float f_min, float f_max,
   fe->t.mel_off = reinterpret_cast<const int*>(d + o_off);
   fe->t.mel_w = reinterpret_cast<const float*>(d + o_w);
   fe->t.n_mels = n_mels; fe->t.nnz = (int)nnz; fe->t.nb16 = nb16;
-  fe->smem_bytes = sizeof(float2) * (kFramesPerCta * kNz + 2 * kNz) +
+  fe->smem_bytes = sizeof(float2) * (kFramesPerCta * kScStride + kTwA + kNz) +
                    sizeof(float) * (kStageSamples + kNfft) + sizeof(int) * 3 * kMaxMels +
                    sizeof(float) * (nnz + 1);
   fe->smem_bytes_edges = fe->smem_bytes + sizeof(float) * (kEdgeStageSamples - kStageSamples);
