@@ -404,6 +404,16 @@ def main():
                 finally:
                     model.precision = precision
 
+    if args.model.startswith("cnn") and precision != "fp32" and not args.no_parity and N_SAMPLES == 16000:
+        # CNN family: hardened weights (no global-mean layer to calibrate on); the timed mode against the fp32 CUDA-core path
+        with torch.no_grad():
+            pw = torch.cat([dev_sets[0][:8192], torch.from_numpy(synth.speechlike(1024, seed=9)).to(dev)])
+            cm = honk2_b200.build_model(args.model, precision=precision)
+            synth.harden_(cm.state_dict())
+            cm = cm.to(dev)
+            par = parity.parity_report(cm, fe, pw, precision)
+            par["inputs"] = "8192 broadband + 1024 speech-like synthetic clips; hardened weights"
+
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import bench_ref

@@ -63,7 +63,8 @@ struct TcCnnParams {
   const __nv_bfloat16* w1;      // [KH1*KW1][4][2][64][8]
   const float* b0;              // [64]
   const float* b1;              // [64]
-  __nv_bfloat16* act;           // [B][H1*8][64]  (position-major: the first Linear's weights are permuted to match)
+  __nv_bfloat16* act;           // [B][4 channel groups][H1*8 positions][16]: a worker warp (32 positions x 16 channels) stores 1 KB
+                                //   contiguous; the first Linear's weights are permuted to this order
   int64_t B;
   TcCnnGeom g;
   int polls;
@@ -331,7 +332,7 @@ cnn_tc_fused_kernel(const TcCnnParams p) {
       mbar_wait_lean(c1_done, it & 1, p.polls);
       tc_fence_after();
       CNN_DBG(d_c1)
-      __nv_bfloat16* act = p.act + b * (int64_t)(g.H1 * 8 * kCnnC) + 16 * cg;
+      __nv_bfloat16* act = p.act + b * (int64_t)(g.H1 * 8 * kCnnC) + (int64_t)cg * (g.H1 * 8 * 16);
       const uint32_t c1col = tmem_base + ((uint32_t)(32 * q) << 16) + 16u * cg;
       for (int t = 0; t < g.tiles1; t += 2) {
         uint32_t va[16], vb[16];
@@ -351,7 +352,7 @@ cnn_tc_fused_kernel(const TcCnnParams p) {
               o[2 * i] = pack_relu_bf16x2(__uint_as_float(v[4 * i]) + bb.x, __uint_as_float(v[4 * i + 1]) + bb.y);
               o[2 * i + 1] = pack_relu_bf16x2(__uint_as_float(v[4 * i + 2]) + bb.z, __uint_as_float(v[4 * i + 3]) + bb.w);
             }
-            uint4* dst = reinterpret_cast<uint4*>(act + (int64_t)(oh * 8 + ow) * kCnnC);
+            uint4* dst = reinterpret_cast<uint4*>(act + (int64_t)(oh * 8 + ow) * 16);
             dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
             dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
           }
@@ -502,13 +503,15 @@ __global__ void pack_cnn_w1_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
-// torch [out][c*M + m] -> bf16 [kLin0N][m*64 + c], rows >= out are zero
+// torch [out][c*M + m] -> bf16 [kLin0N][(c/16)*M*16 + m*16 + c%16] (the order the fused kernel stores), rows >= out are zero
 __global__ void pack_cnn_lin0_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int n_out, int M) {
   const int64_t K = (int64_t)M * kCnnC, total = K * kLin0N;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(i / K);
     const int64_t r = i - n * K;
-    const int m = (int)(r / kCnnC), c = (int)(r - (int64_t)m * kCnnC);
+    const int cg = (int)(r / ((int64_t)M * 16));
+    const int64_t r2 = r - (int64_t)cg * M * 16;
+    const int m = (int)(r2 / 16), c = 16 * cg + (int)(r2 - (int64_t)m * 16);
     out[i] = __float2bfloat16(n < n_out ? w[(int64_t)n * K + (int64_t)c * M + m] : 0.f);
   }
 }
@@ -567,6 +570,7 @@ static bool cnn_tc_plan(TcCnn* p) {
   const int cap = 227 * 1024;
   int ring = (cap - g.off_ring) / kCnnRingUnit;
   if (ring > kCnnMaxRing) ring = kCnnMaxRing;
+  if (const char* e = getenv("HONK2_CNN_RING")) ring = std::min(ring, std::max(2, atoi(e)));   // (experiments: shallower weight ring)
   if (ring > g.units1) ring = g.units1;
   if (ring < 2) return no("shared memory (pooled map + operands leave no room for the weight ring)");
   g.n_ring = ring;
