@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-second-mode", action="store_true")
+    ap.add_argument("--gpu-eager-bar", action="store_true",
+                    help="also time the PyTorch-eager (cuDNN) forward of the reference architecture on this GPU (SURVEY 8d)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     global N_SAMPLES
@@ -431,6 +433,11 @@ def main():
                "sample": f"{n} synthetic {N_SAMPLES / 16000:g} s clips in batches of {args.ref_batch}: numpy compute_mfccs "
                          f"restatement per sample ({fe_s:.1f} s) + PyTorch-CPU fp32 {args.model} forward ({mo_s:.1f} s)"}
 
+    eager = None
+    if args.gpu_eager_bar and world == 1:
+        from oracle import bench_ref
+        eager = bench_ref.gpu_eager_bar(args.model, batch=min(B, 1024 if N_SAMPLES == 16000 else 64), T=1 + N_SAMPLES // 160)
+
     # ---- streaming windows, reported next to the headline: B windows of 1 s at a 10 ms shift
     # (gsc_dev_config.json:62-63) from one resident stream; front-end alone and front-end + network.
     streaming = None
@@ -486,7 +493,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 4,
                     "d2h_bytes_per_step": B * model.n_labels * 4, "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "roofline": roof, "frontend_roofline": fe_roof, "parity": par,
-            "parity_mode": second, "cpu_baseline": cpu, "streaming_windows": streaming,
+            "parity_mode": second, "cpu_baseline": cpu, "gpu_eager_bar": eager, "streaming_windows": streaming,
             "strong_scaling": strong, "numa": numa_info,
             "tensor_frac_of_burst_peak_whole_step": FLOPS_PER_UTT.get(args.model, 0) * value / world / 1e12 / pk["bf16_tflops"]}
     print(json.dumps(line))
