@@ -160,12 +160,14 @@ def run_reference_arm(args):
         t_fe += a; t_model += b
     dt = time.perf_counter() - t0
     value = batch * args.steps / dt
-    sample = (f"{args.steps} steps x {batch} synthetic {N_SAMPLES / 16000:g} s clips: numpy restatement of compute_mfccs per "
+    sample = (f"each step is a bounded sample of the workload: {batch} of its {args.batch} synthetic {N_SAMPLES / 16000:g} s clips "
+              f"(the reference's own configured batch size), {args.steps} steps: numpy restatement of compute_mfccs per "
               f"sample + PyTorch-CPU fp32 restatement of {args.model} forward; front-end {t_fe:.2f} s, model {t_model:.2f} s")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, batch),
+            # the SAME workload as the GPU arm (its `config`); `sample_per_step` is what one timed step of this arm covers
+            "config": dict(workload_config(args, args.batch), sample_per_step=batch),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
