@@ -236,27 +236,30 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
   }
   __syncwarp();
 
-  // ---- stage B: 16 DFT-15 over n2 (lane = k1): Z[k1 + 16 k2]
+  // ---- stage B: 16 DFT-15 over n2 (lane = k1): Z[k1 + 16 k2] stays in this lane's registers
+  float2 z[15];
   {
-    float2 y[15], z[15];
+    float2 y[15];
 #pragma unroll
     for (int n2 = 0; n2 < 15; ++n2) y[n2] = sc[l * 15 + n2];
-    __syncwarp();
     dft15(y, z);
-#pragma unroll
-    for (int k2 = 0; k2 < 15; ++k2) sc[l + 16 * k2] = z[k2];
   }
-  __syncwarp();
 
-  // ---- real-FFT split + power: X[k] = E + (-sin, -cos)(theta_k) * O
+  // ---- real-FFT split + power: X[k] = E + (-sin, -cos)(theta_k) * O for k = l + 16 j.  Z[k] is this lane's z[j];
+  // its mirror Z[240 - k] = Z[(16 - l) + 16 (14 - j)] is lane 16 - l's z[14 - j] (one shuffle inside the half-warp),
+  // or, for lane 0, its own z[(15 - j) mod 15]: no trip through shared memory.
   float p[15];
+  const int mirror = (16 - l) & 15;
 #pragma unroll
   for (int j = 0; j < 15; ++j) {
     p[j] = 0.f;
     if (j < tb.nb16) {
       const int k = l + 16 * j;
-      const float2 zk = sc[k];
-      const float2 zm = sc[(kNz - k) % kNz];
+      const float2 zk = z[j];
+      float2 zm;
+      zm.x = __shfl_sync(0xffffffffu, z[14 - j].x, mirror, 16);
+      zm.y = __shfl_sync(0xffffffffu, z[14 - j].y, mirror, 16);
+      if (l == 0) zm = z[(15 - j) % 15];
       const float2 tw = s_tw480[k];  // (sin, cos)
       const float er = 0.5f * (zk.x + zm.x), ei = 0.5f * (zk.y - zm.y);
       const float orr = 0.5f * (zk.x - zm.x), oi = 0.5f * (zk.y + zm.y);
