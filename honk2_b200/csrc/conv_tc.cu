@@ -1177,8 +1177,8 @@ static TcSweepPlan tc_sweep_plan(const TcResNet* p, int H, int W, bool split) {
   f.w_off[0] = f.c0w_off + round_up(3 * 2 * 3 * p->CP * 16, 128);
   f.w_off[1] = split ? f.w_off[0] : f.w_off[0] + round_up(w_bytes, 128);   // (split: one buffer, see the kernel)
   f.skip_off = round_up(f.w_off[1] + w_bytes, 1024);
-  f.pool_off = f.skip_off + (split ? 0 : p->NKC * p->NP * 2048);   // one skip slot per epilogue warp group
-  f.ring_off = f.pool_off + (f.pack_n > 1 ? round_up(f.pack_n * 4 * p->NKC * p->CP * 4, 1024) : 0);   // packed: pooled sums per stacked utterance
+  f.pool_off = f.skip_off + (split ? 0 : sw_groups(p->NKC) * p->NP * 2048);   // one skip slot per epilogue warp group
+  f.ring_off = f.pool_off + (f.packed ? round_up(f.pack_n * sw_epi_warps(p->NKC) * p->CP * 4, 1024) : 0);   // packed: pooled sums per stacked utterance
   // rows per chunk of a staged column.  The split mode stages twice the chunks: its chunks are cut down to the rows
   // the map's own lanes read (H + 2 dmax); the lanes past the map then read into the next chunk / the slack.
   const int full_rows = (128 + 2 * dmax + 7) & ~7;

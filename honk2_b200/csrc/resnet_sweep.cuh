@@ -59,7 +59,12 @@ constexpr int kSwMaxW = 256;
 constexpr int kSwTraceLen = 2048;   // steps / blocks recorded by the event trace
 constexpr int kSwWeightStep = 12;   // producer step of a layer at which the NEXT layer's weights are requested
 
-__host__ __device__ constexpr int sw_epi_warps(int NKC) { return 4 * NKC; }
+// Epilogue warp groups (4 warps = the four TMEM lane quarters each).  A group owns every sw_groups-th output block and handles all
+// of its channels; what a group spends per block hardly depends on the channel count (barrier wait, TMEM round trips, skip
+// staging, publishing), so the narrow nets (NKC = 1, 2) get three groups too: with two they were epilogue bound (ncu: tensor pipe
+// 38 % active, 680 cycles per step against 336 of MMAs).
+__host__ __device__ constexpr int sw_groups(int NKC) { return NKC < 3 ? 3 : NKC; }
+__host__ __device__ constexpr int sw_epi_warps(int NKC) { return 4 * sw_groups(NKC); }
 __host__ __device__ constexpr int sw_threads(int NKC) { return 32 * (kSwFrontWarps + sw_epi_warps(NKC)); }
 
 // control block layout (bytes from the start of dynamic shared memory)
@@ -78,7 +83,7 @@ constexpr int kSwKc = round_up(kSwTmemSlot + 4, 128);          // [1 + n_layers]
 constexpr int kSwKcBytes = 6144;
 constexpr int kSwPool = kSwKc + kSwKcBytes;                    // [12 epilogue warps][48] f32: every warp's share of the pooled sums
 constexpr int kSwCtrlBytes = round_up(kSwPool + 12 * 48 * 4, 1024);
-// (epilogue warp group g = warp / 4, one warp per TMEM lane quarter, owns the blocks = g mod NKC: there are NKC groups)
+// (epilogue warp group g = warp / 4, one warp per TMEM lane quarter, owns the blocks = g mod sw_groups(NKC))
 
 struct SwParams {
   // Per-layer data is derived from kernel parameters only (constant bank => warp-uniform for the compiler, which
@@ -141,6 +146,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
   static_assert(K32 || !SPLIT, "the split-bf16 mode is built on the 32-byte-row layout");
   constexpr int NA = SPLIT ? 2 * NKC : NKC;            // activation chunks staged per column (SPLIT: hi chunks, then lo chunks)
   constexpr int kEpiWarps = sw_epi_warps(NKC);
+  constexpr int NG = sw_groups(NKC);
   constexpr int kEpiThreads = 32 * kEpiWarps;
   constexpr int CP = 16 * NKC;
   constexpr int NP = 2 * NKC;
@@ -229,7 +235,8 @@ resnet_tc_sweep_kernel(const SwParams p) {
   // starts zeroed and the epilogue re-zeroes each block right after reading it.
   if (warp < kEpiWarps) {
     const int q = warp & 3, j = warp >> 2;
-    for (int a = 0; a < NB; ++a) tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * CP + 16 * j));
+    if (j < NKC)   // (the narrow nets have more warp groups than 16-column chunks)
+      for (int a = 0; a < NB; ++a) tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * CP + 16 * j));
     tmem_st_wait();
   }
   tc_fence_before();
@@ -732,7 +739,7 @@ resnet_tc_sweep_kernel(const SwParams p) {
                 it.Lr = (W - it.r + d - 1) / d;
               }
               if (++esl == NB) { esl = 0; epr ^= 1u; }
-              if (++eown == NKC) eown = 0;
+              if (++eown == NG) eown = 0;
               if (mine) break;
             }
             return ob;
