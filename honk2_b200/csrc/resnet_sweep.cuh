@@ -679,6 +679,10 @@ resnet_tc_sweep_kernel(const SwParams p) {
     int gblk = 0;
     long long e_wait = 0, e_tmem = 0, e_pub = 0, e_math = 0, e_conv0 = 0, e_t = clock64();
     for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+      // Block ownership restarts with every utterance: which warp group sums which columns of the last layer then does
+      // not depend on how many blocks this CTA has processed before, so an utterance's pooled sums -- and logits -- are
+      // bit-identical wherever it sits in the batch (tests: full-batch permutation invariance).
+      eown = 0;
       for (int ll = ll0; ll < nl1; ++ll, ++sq) {
         const bool is_c0 = ll == 0;      // conv_0 + ReLU -> P (resnet.py:40-41): no skip, no constant
         const int l = ll - 1;

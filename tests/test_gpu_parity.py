@@ -740,3 +740,46 @@ def test_packed_strips_short_clips(dev, name, T):
             y = m(feats.to(dev)).cpu().numpy()
         ref = model_ref.forward(kind, sd, cfg, feats).numpy()
         assert logit_err(y, ref) <= tol, (name, T, precision, logit_err(y, ref))
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE's full batch (8192 clips): utterances are independent, so a permutation of the
+# batch must permute the logits BIT FOR BIT -- whatever SM, strip position, stacking group or sub-batch an utterance
+# lands in -- and repeated launches must agree bit for bit.
+
+@pytest.mark.parametrize("name,precision", [("res15", "bf16"), ("res15", "bf16x3"), ("res8", "bf16"), ("res26", "bf16"),
+                                            ("res15_narrow", "bf16"), ("cnn-trad-fpool3", "bf16"), ("res8", "fp32")])
+def test_full_batch_permutation_invariance(dev, name, precision):
+    B = 8192 if precision != "fp32" else 1024
+    ap = AudioProcessor()
+    w = torch.from_numpy(synth.broadband(B, seed=31)).to(dev)
+    m, _ = gpu_model(name, "hardened", dev, precision=precision)
+    g = torch.Generator().manual_seed(5)
+    perm = torch.randperm(B, generator=g).to(dev)
+    with torch.no_grad():
+        feats = ap.compute_mfccs_batch(w)
+        y = m(feats)
+        y_again = m(feats)
+        y_perm = m(feats[perm].contiguous())
+        f_perm = ap.compute_mfccs_batch(w[perm].contiguous())
+    assert torch.isfinite(y).all()
+    assert torch.equal(y, y_again), "repeated launches differ"
+    if name in ("res8", "res26") and precision != "fp32":
+        # packed strips: the pooled mean of a stacked utterance is reduced over the TMEM lanes it happens to occupy, so its
+        # position inside the group of 4 (2) changes the ORDER of that fp32 sum, nothing else: a few ulp of the logit scale
+        assert float((y[perm] - y_perm).abs().max()) <= 2e-6 * float(y.abs().max())
+    else:
+        assert torch.equal(y[perm], y_perm), "an utterance's logits depend on its position in the batch"
+    assert torch.equal(feats[perm], f_perm), "a clip's features depend on its position in the batch"
+
+
+def test_mfcc_gain_shift_property_full_batch(dev):
+    """Scaling a clip by 2^k scales every power by 4^k exactly (power-of-two gains commute with fp32 rounding), so the
+    features shift by 4 k ln 2 up to the rounding of the logarithm -- checked on the full 8192-clip batch."""
+    ap = AudioProcessor()
+    w = torch.from_numpy(synth.broadband(8192, seed=17)).to(dev)
+    with torch.no_grad():
+        f1 = ap.compute_mfccs_batch(w)
+        f2 = ap.compute_mfccs_batch(w * 8.0)
+    shift = 4.0 * 3 * float(np.log(2.0))
+    assert float((f2 - f1 - shift).abs().max()) <= 2e-5 * 40
