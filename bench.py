@@ -22,6 +22,9 @@ One "step" = one pass of the hot path over one batch of synthetic waveforms per 
             the classes are spread (honk2_b200.parity).
   parity_mode  the same measurements for the other tensor-core precision (bf16x3 when the headline runs bf16): the
             mode that meets the fp32 tolerance, driver-visible next to the headline.
+  other_configs  the other BASELINE.json configurations (res8, res26, res15-narrow, cnn-trad-fpool3, res15 in fp32, res15
+            on 9 s clips), five device-resident steps each with their own roofline object, so that one driver run sees them.
+  e2e_pcm16 the e2e path fed with int16 PCM host buffers (the wav files' own sample format; bit-identical logits).
   cpu_baseline  the oracle port (oracle/: the reference algorithm in numpy / PyTorch-CPU fp32) timed on this host's
             cores on a bounded sample.
 """
@@ -236,6 +239,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-second-mode", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short device-resident runs of the other BASELINE.json configurations (`other_configs`)")
     ap.add_argument("--gpu-eager-bar", action="store_true",
                     help="also time the PyTorch-eager (cuDNN) forward of the reference architecture on this GPU (SURVEY 8d)")
     args = ap.parse_args()
@@ -281,6 +286,7 @@ def main():
     # synthetic data: two distinct batches (each 524 MB > L2), device resident for `value`
     n_sets = 2
     host_sets = [torch.from_numpy(synth.broadband(B_cfg, N=N_SAMPLES, seed=100 * rank + s)).pin_memory() for s in range(n_sets)]
+    host_f32 = host_sets
     dev_sets = [h.to(dev) for h in host_sets]
     targets = torch.randint(0, model.n_labels, (B_cfg,), device=dev)
 
@@ -323,11 +329,12 @@ def main():
         th1 = time.perf_counter()
         return max_over_ranks(e0.elapsed_time(e1)), launches, (th0, th1)
 
-    def timed_e2e(per_gpu, steps):
+    def timed_e2e(per_gpu, steps, hosts=None):
         """pinned host waveforms -> H2D -> forward_wave -> logits D2H, pipelined; every step's result is complete (event)
-        before its host buffer is handed out again."""
+        before its host buffer is handed out again.  `hosts`: other pinned host batches (the int16 PCM form)."""
+        host_sets = hosts if hosts is not None else host_f32
         pipe = HostPipeline(model, fe, N_SAMPLES, sub_batch=min(args.e2e_sub_batch, per_gpu), device=dev,
-                            slots=args.e2e_slots)
+                            slots=args.e2e_slots, dtype=host_sets[0].dtype)
         outs = [torch.empty((per_gpu, model.n_labels), dtype=torch.float32).pin_memory() for _ in range(2)]
         pending = [None, None]
 
@@ -361,6 +368,11 @@ def main():
         value = B * world * K / (ms / 1e3)
         ms_e2e = timed_e2e(B, K)
         e2e_value = B * world * K / (ms_e2e / 1e3)
+        # the same end-to-end path fed with 16-bit PCM samples, the format of the wav files behind the reference's
+        # datasets (librosa returns float32(s / 32768) for them): half the host->device bytes, bit-identical logits
+        host_pcm = [(h * 32768.0).round().clamp(-32768, 32767).to(torch.int16).pin_memory() for h in host_f32]
+        ms_e2e_pcm = timed_e2e(B, K, hosts=host_pcm)
+        del host_pcm
 
         strong = None
         if world > 1 and args.scaling == "weak":
@@ -417,6 +429,56 @@ def main():
             cm = cm.to(dev)
             par = parity.parity_report(cm, fe, pw, precision)
             par["inputs"] = "8192 broadband + 1024 speech-like synthetic clips; hardened weights"
+
+    # ---- the other BASELINE.json configurations, device-resident, a few steps each, in the same driver-visible line
+    others = None
+    if world == 1 and not args.no_other_configs and args.model == "res15" and N_SAMPLES == 16000:
+        others = []
+        plan = [("res8", "bf16", 8192, 16000, "configs[0] on the GPU"), ("res15", "fp32", 2048, 16000, "configs[1], fp32 half"),
+                ("res15", "bf16x3", 8192, 16000, "configs[1], fp32-grade tensor-core mode"),
+                ("res26", "bf16", 8192, 16000, "configs[2]"), ("res15_narrow", "bf16", 8192, 16000, "configs[2]"),
+                ("res15_narrow", "fp32", 2048, 16000, "configs[2], CUDA-core path"),
+                ("cnn-trad-fpool3", "bf16", 8192, 16000, "configs[3]"),
+                ("res15", "bf16", 1024, 144000, "configs[4], one GPU's view: hey_snips-shaped 9 s clips")]
+        for name, prec, nb, ns, tag in plan:
+            if prec == precision and name == args.model and ns == N_SAMPLES:
+                continue
+            if second is not None and name == args.model and prec == second["precision"] and ns == N_SAMPLES:
+                continue   # already in `parity_mode`
+            try:
+                with torch.no_grad():
+                    mo = honk2_b200.build_model(name, precision=prec).to(dev)
+                    # the resident synthetic waveforms again (no host-side generation): 1 s clips as they are, the 9 s clips
+                    # cut from the two sets laid end to end (synthetic broadband noise either way)
+                    if ns == N_SAMPLES:
+                        ws = [d[:nb] for d in dev_sets]
+                    else:
+                        flat = torch.cat([d.reshape(-1) for d in dev_sets])
+                        ws = [flat[o:o + nb * ns].view(nb, ns) for o in (0, 8000)]
+                    out = torch.empty((nb, mo.n_labels), dtype=torch.float32, device=dev)
+                    for i in range(3):
+                        mo.forward_wave(ws[i & 1], fe, out=out)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ko = 5
+                    e0.record()
+                    for i in range(ko):
+                        mo.forward_wave(ws[i & 1], fe, out=out)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms_o = e0.elapsed_time(e1)
+                    pr = honk2_b200.profile_layers(mo, fe, ws, ko)
+                    rf = roofline_for(pr, prec, pk, nb, ko)
+                    others.append({"model": name, "precision": prec, "batch": nb, "clip_samples": ns, "baseline_config": tag,
+                                   "value": nb * ko / (ms_o / 1e3), "unit": UNIT, "ms_per_step": ms_o / ko, "steps": ko,
+                                   "roofline": None if rf is None else {k: rf[k] for k in (
+                                       "bound", "achieved", "peak", "unit", "frac", "frac_of_burst_peak", "kernel",
+                                       "avg_launch_ms", "share_of_step", "frontend_ms_per_step")}})
+                    del mo, ws, out
+                    flat = None
+                    torch.cuda.empty_cache()
+            except Exception as exc:   # one configuration failing must not lose the headline line
+                others.append({"model": name, "precision": prec, "batch": nb, "clip_samples": ns, "error": repr(exc)[:300]})
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -494,9 +556,13 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 4,
                     "d2h_bytes_per_step": B * model.n_labels * 4, "ms_per_step": ms_e2e / K},
+            "e2e_pcm16": {"value": B * world * K / (ms_e2e_pcm / 1e3), "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 2,
+                          "d2h_bytes_per_step": B * model.n_labels * 4, "ms_per_step": ms_e2e_pcm / K,
+                          "note": "host waveforms as int16 PCM (the wav files' format) through kws_model_forward_wave_pcm16; "
+                                  "same synthetic clips rounded to 16 bits"},
             "gpu_launches": launches, "roofline": roof, "frontend_roofline": fe_roof, "parity": par,
             "parity_mode": second, "cpu_baseline": cpu, "gpu_eager_bar": eager, "streaming_windows": streaming,
-            "strong_scaling": strong, "numa": numa_info,
+            "strong_scaling": strong, "numa": numa_info, "other_configs": others,
             "tensor_frac_of_burst_peak_whole_step": FLOPS_PER_UTT.get(args.model, 0) * value / world / 1e12 / pk["bf16_tflops"]}
     print(json.dumps(line))
     if world > 1:

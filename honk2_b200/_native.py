@@ -49,6 +49,7 @@ SIGNATURES = {
     "kws_frontend_n_frames": (C.c_int, [C.c_void_p, C.c_int]),
     "kws_frontend_n_mels": (C.c_int, [C.c_void_p]),
     "kws_mfcc_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "kws_mfcc_forward_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "kws_mfcc_stream_scratch_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int, C.c_int]),
     "kws_mfcc_stream_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_size_t, C.c_void_p]),
@@ -64,6 +65,8 @@ SIGNATURES = {
     "kws_model_wave_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int]),
     "kws_model_forward_wave": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kws_model_forward_wave_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                               C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kws_model_last_launches": (C.c_int64, [C.c_void_p]),
     "kws_model_kernel_path": (C.c_char_p, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "kws_eval_accumulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

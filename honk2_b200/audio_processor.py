@@ -65,12 +65,18 @@ class AudioProcessor(object):
 
     # ---- batched GPU API -----------------------------------------------------------------
     def compute_mfccs_batch(self, waves, out=None):
-        """waves: CUDA float32 [B, N] (contiguous) -> CUDA float32 [B, T, n_mels]."""
+        """waves: CUDA float32 [B, N] (contiguous) -> CUDA float32 [B, T, n_mels].
+
+        int16 waveforms are taken as 16-bit PCM, the samples of the wav files behind the reference's datasets
+        (librosa.core.load returns float32(s / 32768) for them, dataset/dataset_utils.py:20,51): the kernel converts while
+        it stages, the features are bit-identical to those of the converted floats, and the waveforms cost half the
+        host->device and HBM bytes."""
         if not (isinstance(waves, torch.Tensor) and waves.is_cuda):
             raise _native.NativeError("compute_mfccs_batch needs a CUDA tensor: there is no CPU path")
         if waves.dim() != 2:
             raise ValueError("compute_mfccs_batch expects waveforms shaped [B, N]")
-        if waves.dtype != torch.float32:
+        pcm16 = waves.dtype == torch.int16
+        if not pcm16 and waves.dtype != torch.float32:
             waves = waves.float()
         waves = waves.contiguous()
         B, N = waves.shape
@@ -83,8 +89,9 @@ class AudioProcessor(object):
         lib = _native.load()
         fe = self._frontend(waves.device)
         with torch.cuda.device(waves.device):
-            _native.check(lib.kws_mfcc_forward(fe, C.c_void_p(waves.data_ptr()), B, N, C.c_void_p(out.data_ptr()),
-                                               _stream_ptr(waves.device)), "kws_mfcc_forward")
+            fn = lib.kws_mfcc_forward_pcm16 if pcm16 else lib.kws_mfcc_forward
+            _native.check(fn(fe, C.c_void_p(waves.data_ptr()), B, N, C.c_void_p(out.data_ptr()),
+                             _stream_ptr(waves.device)), "kws_mfcc_forward_pcm16" if pcm16 else "kws_mfcc_forward")
         return out
 
     # ---- streaming windows -------------------------------------------------------------

@@ -24,6 +24,7 @@ struct Conv3x3F32 {
   const float* bn_shift; // [C] -mean*scale
   int64_t B;
   int C, H, W, d;
+  int resident = 1;      // 0: never the resident-weight persistent kernel (HONK2_F32_RESIDENT=0, read per model handle)
 };
 int launch_conv3x3_f32(const Conv3x3F32& a, cudaStream_t st);
 // Q (output channels per thread) the conv3x3 kernel uses for C maps, and the padded row width.

@@ -128,9 +128,16 @@ __device__ __forceinline__ void dft15(const float2 (&y)[15], float2 (&z)[15]) {
 // for a dense [B, N] batch, = the shift for overlapping windows of a stream).
 // EDGES = true (streaming front-end): a CTA computes the four frames of four windows that touch the reflect padding
 // (t = 0, 1, T-2, T-1); every other frame of a window is shared with the stream-level frame table.
-template <bool EDGES>
+//
+// SMP = float: waveforms as the reference's loader hands them over (librosa float32 in [-1, 1)).  SMP = int16_t: the 16-bit
+// PCM samples as they sit in the wav files (dataset/dataset_utils.py loads them through librosa, which returns exactly
+// s / 32768): converted while staging, bit-identical features, half the bytes from the host and from HBM.
+__device__ __forceinline__ float smp_ld(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float smp_ld(const int16_t* p) { return (float)__ldg(p) * (1.f / 32768.f); }
+
+template <bool EDGES, typename SMP>
 __global__ void __launch_bounds__(kMfccThreads)
-mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride, int64_t B, int N, int T,
+mfcc_kernel(FrontendTables tb, const SMP* __restrict__ wav, int64_t wav_stride, int64_t B, int N, int T,
             int tiles_per_utt, float* __restrict__ feat) {
   constexpr int kStage = EDGES ? kEdgeStageSamples : kStageSamples;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -147,7 +154,7 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
   const int tid = threadIdx.x;
   const int64_t b = EDGES ? (int64_t)blockIdx.x * 4 : blockIdx.x / tiles_per_utt;   // (EDGES: first of four windows)
   const int t0 = EDGES ? 0 : (blockIdx.x % tiles_per_utt) * kFramesPerCta;
-  const float* w = wav + b * wav_stride;
+  const SMP* w = wav + b * wav_stride;
 
   if constexpr (EDGES) {
     // frame slot s = 4 * (window - b) + e, e -> frame t = 0, 1, T-2, T-1: samples [160 t - 240, +480) of its window
@@ -159,7 +166,7 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
       if (j < 0) j = -j;
       if (j >= N) j = 2 * (N - 1) - j;
       j = max(0, min(j, N - 1));
-      s_wave[i] = b + wi < B ? __ldg(w + (int64_t)wi * wav_stride + j) : 0.f;
+      s_wave[i] = b + wi < B ? smp_ld(w + (int64_t)wi * wav_stride + j) : 0.f;
     }
   } else {
     // stage: samples [160*t0 - 240, +2880) with librosa 'reflect' padding at the clip edges; only the frames that exist
@@ -168,25 +175,36 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
     const int n_fr = min(kFramesPerCta, T - t0);
     const int n_stage = (n_fr - 1) * kHop + kNfft;
     const bool vec = ((reinterpret_cast<uintptr_t>(w) & 15) == 0);   // (j0 is a multiple of 16 samples)
+    constexpr int V = 16 / (int)sizeof(SMP);   // samples per 16-byte load (n_stage is a multiple of 8)
     if (vec) {
-      for (int i4 = tid; i4 < (n_stage >> 2); i4 += kMfccThreads) {
-        const int i = i4 << 2, j = j0 + i;
-        float4 v;
-        if (j >= 0 && j + 3 < N) {
-          v = __ldg(reinterpret_cast<const float4*>(w + j));
-        } else {
-          float e[4];
+      for (int iv = tid; iv < n_stage / V; iv += kMfccThreads) {
+        const int i = iv * V, j = j0 + i;
+        float e[V];
+        if (j >= 0 && j + V - 1 < N) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(w + j));
+          if constexpr (sizeof(SMP) == 4) {
+            e[0] = __uint_as_float(raw.x); e[1] = __uint_as_float(raw.y); e[2] = __uint_as_float(raw.z); e[3] = __uint_as_float(raw.w);
+          } else {
+            const uint32_t r[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 4; ++q) {
+              e[2 * q] = (float)(int16_t)(r[q] & 0xFFFFu) * (1.f / 32768.f);
+              e[2 * q + 1] = (float)(int16_t)(r[q] >> 16) * (1.f / 32768.f);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < V; ++q) {
             int jj = j + q;
             if (jj < 0) jj = -jj;
             if (jj >= N) jj = 2 * (N - 1) - jj;
             jj = max(0, min(jj, N - 1));  // only reachable for samples of masked frames
-            e[q] = __ldg(w + jj);
+            e[q] = smp_ld(w + jj);
           }
-          v = make_float4(e[0], e[1], e[2], e[3]);
         }
-        *reinterpret_cast<float4*>(s_wave + i) = v;
+#pragma unroll
+        for (int q = 0; q < V; q += 4)
+          *reinterpret_cast<float4*>(s_wave + i + q) = make_float4(e[q], e[q + 1], e[q + 2], e[q + 3]);
       }
     } else {
       for (int i = tid; i < n_stage; i += kMfccThreads) {
@@ -194,7 +212,7 @@ mfcc_kernel(FrontendTables tb, const float* __restrict__ wav, int64_t wav_stride
         if (j < 0) j = -j;
         if (j >= N) j = 2 * (N - 1) - j;
         j = max(0, min(j, N - 1));
-        s_wave[i] = __ldg(w + j);
+        s_wave[i] = smp_ld(w + j);
       }
     }
   }
@@ -413,9 +431,11 @@ extern "C" int kws_frontend_create(int sr, int n_mels, float f_min, float f_max,
                    sizeof(float) * (kStageSamples + kNfft) + sizeof(int) * 3 * kMaxMels +
                    sizeof(float) * (nnz + 1);
   fe->smem_bytes_edges = fe->smem_bytes + sizeof(float) * (kEdgeStageSamples - kStageSamples);
-  e = cudaFuncSetAttribute(mfcc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes);
+  e = cudaFuncSetAttribute(mfcc_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(mfcc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes_edges);
+    e = cudaFuncSetAttribute(mfcc_kernel<false, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(mfcc_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes_edges);
   if (e != cudaSuccess) {
     set_error("kws_frontend_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     cudaFree(fe->dev_blob);
@@ -439,23 +459,33 @@ extern "C" int kws_frontend_n_frames(const kws_frontend_t* fe, int n_samples) {
 
 extern "C" int kws_frontend_n_mels(const kws_frontend_t* fe) { return fe ? fe->n_mels : 0; }
 
-extern "C" int kws_mfcc_forward(const kws_frontend_t* fe, const float* wav, int64_t B, int n_samples,
-                                float* feat, void* stream) {
-  KWS_REQUIRE(fe != nullptr, "kws_mfcc_forward: frontend is null");
-  KWS_REQUIRE(B >= 0, "kws_mfcc_forward: negative batch");
+template <typename SMP>
+static int mfcc_forward_any(const char* who, const kws_frontend_t* fe, const SMP* wav, int64_t B, int n_samples, float* feat,
+                            void* stream) {
+  KWS_REQUIRE(fe != nullptr, "%s: frontend is null", who);
+  KWS_REQUIRE(B >= 0, "%s: negative batch", who);
   // librosa's reflect padding of n_fft/2 needs more than n_fft/2 samples
-  KWS_REQUIRE(n_samples > kNfft / 2, "kws_mfcc_forward: need more than %d samples per clip (got %d)",
-              kNfft / 2, n_samples);
+  KWS_REQUIRE(n_samples > kNfft / 2, "%s: need more than %d samples per clip (got %d)", who, kNfft / 2, n_samples);
   if (B == 0) return KWS_OK;
-  KWS_REQUIRE(wav != nullptr && feat != nullptr, "kws_mfcc_forward: null buffer");
+  KWS_REQUIRE(wav != nullptr && feat != nullptr, "%s: null buffer", who);
   const int T = 1 + n_samples / kHop;
   const int tiles = ceil_div(T, kFramesPerCta);
   const int64_t blocks = B * tiles;
-  KWS_REQUIRE(blocks < (int64_t)2147483647, "kws_mfcc_forward: batch too large for one launch");
-  mfcc_kernel<false><<<(unsigned)blocks, kMfccThreads, fe->smem_bytes, as_stream(stream)>>>(
+  KWS_REQUIRE(blocks < (int64_t)2147483647, "%s: batch too large for one launch", who);
+  mfcc_kernel<false, SMP><<<(unsigned)blocks, kMfccThreads, fe->smem_bytes, as_stream(stream)>>>(
       fe->t, wav, (int64_t)n_samples, B, n_samples, T, tiles, feat);
   KWS_CHECK_LAUNCH();
   return KWS_OK;
+}
+
+extern "C" int kws_mfcc_forward(const kws_frontend_t* fe, const float* wav, int64_t B, int n_samples,
+                                float* feat, void* stream) {
+  return mfcc_forward_any<float>("kws_mfcc_forward", fe, wav, B, n_samples, feat, stream);
+}
+
+extern "C" int kws_mfcc_forward_pcm16(const kws_frontend_t* fe, const int16_t* wav, int64_t B, int n_samples,
+                                      float* feat, void* stream) {
+  return mfcc_forward_any<int16_t>("kws_mfcc_forward_pcm16", fe, wav, B, n_samples, feat, stream);
 }
 
 extern "C" size_t kws_mfcc_stream_scratch_bytes(const kws_frontend_t* fe, int64_t n_windows, int window, int shift) {
@@ -483,7 +513,7 @@ extern "C" int kws_mfcc_stream_forward(const kws_frontend_t* fe, const float* wa
     // windows do not share frames (or have no interior frame): every window in full, read in place from the stream
     const int64_t blocks = n_windows * tiles;
     KWS_REQUIRE(blocks < (int64_t)2147483647, "kws_mfcc_stream_forward: too many windows for one launch");
-    mfcc_kernel<false><<<(unsigned)blocks, kMfccThreads, fe->smem_bytes, st>>>(
+    mfcc_kernel<false, float><<<(unsigned)blocks, kMfccThreads, fe->smem_bytes, st>>>(
         fe->t, wav, (int64_t)shift, n_windows, window, T, tiles, feat);
     KWS_CHECK_LAUNCH();
     return KWS_OK;
@@ -496,11 +526,11 @@ extern "C" int kws_mfcc_stream_forward(const kws_frontend_t* fe, const float* wa
   // 1) the frame table of the whole span as ONE clip: rows 2 .. J-3 do not touch its reflect padding
   float* S = static_cast<float*>(scratch);
   const int J = 1 + (int)(span / kHop);
-  mfcc_kernel<false><<<(unsigned)ceil_div(J, kFramesPerCta), kMfccThreads, fe->smem_bytes, st>>>(
+  mfcc_kernel<false, float><<<(unsigned)ceil_div(J, kFramesPerCta), kMfccThreads, fe->smem_bytes, st>>>(
       fe->t, wav, span, (int64_t)1, (int)span, J, ceil_div(J, kFramesPerCta), S);
   KWS_CHECK_LAUNCH();
   // 2) the four frames per window that do (reflect padding at the WINDOW's edges, audio_processor.py:19-26 per window)
-  mfcc_kernel<true><<<(unsigned)ceil_div<int64_t>(n_windows, 4), kMfccThreads, fe->smem_bytes_edges, st>>>(
+  mfcc_kernel<true, float><<<(unsigned)ceil_div<int64_t>(n_windows, 4), kMfccThreads, fe->smem_bytes_edges, st>>>(
       fe->t, wav, (int64_t)shift, n_windows, window, T, 1, feat);
   KWS_CHECK_LAUNCH();
   // 3) interior frames: copies of table rows

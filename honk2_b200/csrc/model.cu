@@ -21,6 +21,7 @@ struct Model {
   bool weights_set = false;
   int64_t last_launches = 0;
   int chunk[3] = {0, 0, 0};   // per precision
+  bool f32_resident = true;   // fp32 C -> C layers on the resident-weight persistent kernel (HONK2_F32_RESIDENT=0: the tile-per-CTA kernel)
   LaunchProfiler prof;
 
   // ---- ResNet fp32 packed weights
@@ -120,6 +121,7 @@ extern "C" int kws_resnet_create(const kws_resnet_config* cfg, kws_model_t** out
   kws_model* m = new kws_model();
   m->kind = KIND_RESNET;
   m->rc = *cfg;
+  { const char* e = getenv("HONK2_F32_RESIDENT"); m->f32_resident = !(e && e[0] == '0'); }
   const int C = cfg->n_maps, n = cfg->n_layers, L = cfg->n_labels;
   const int Q = conv3x3_f32_q(C), CG = ceil_div(C, Q);
   BlobPlan bp;
@@ -193,8 +195,10 @@ static void resnet_map(const kws_resnet_config& c, int T, int F, int* H, int* W)
 
 static int64_t default_chunk(const Model* m, int precision, int64_t per_utt_bytes) {
   if (m->chunk[precision] > 0) return m->chunk[precision];
-  // keep the three live activation tensors of a chunk well inside the 126 MB L2
-  int64_t c = (72ll << 20) / (3 * std::max<int64_t>(per_utt_bytes, 1));
+  // The fp32 CUDA-core path is FMA-bound (a layer moves ~2.2 MB per utterance through DRAM at < 10 % of the HBM
+  // bandwidth), so its sub-batch only has to be large enough that the persistent convolution kernel's last wave is a
+  // small fraction of a launch: ~2 GB of activations.
+  int64_t c = (2048ll << 20) / (3 * std::max<int64_t>(per_utt_bytes, 1));
   if (c < 8) c = 8;
   if (c > 4096) c = 4096;
   return c;
@@ -246,6 +250,7 @@ static int resnet_forward_f32(Model* m, const float* feat, int64_t B, int T, int
       a.bn_scale = m->r_bn_scale[i - 1];
       a.bn_shift = m->r_bn_shift[i - 1];
       a.B = nb; a.C = C; a.H = H; a.W = W; a.d = resnet_dilation(c, i);
+      a.resident = m->f32_resident ? 1 : 0;
       m->prof.tick(0, st);
       KWS_TRY(launch_conv3x3_f32(a, st));
       x = pp[flip];
@@ -532,17 +537,18 @@ extern "C" size_t kws_model_wave_workspace_bytes(const kws_model_t* m, const kws
   return model_ws + round_up<size_t>((size_t)B * T * F * sizeof(float), 256);
 }
 
-extern "C" int kws_model_forward_wave(kws_model_t* m, const kws_frontend_t* fe, const float* wav, int64_t B,
-                                      int n_samples, float* logits, int precision, void* workspace,
-                                      size_t workspace_bytes, void* stream) {
-  KWS_REQUIRE(m != nullptr && fe != nullptr, "kws_model_forward_wave: null handle");
-  KWS_REQUIRE(B >= 0, "kws_model_forward_wave: negative batch");
+template <typename SMP>
+static int model_forward_wave_any(const char* who, kws_model_t* m, const kws_frontend_t* fe, const SMP* wav, int64_t B,
+                                  int n_samples, float* logits, int precision, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  KWS_REQUIRE(m != nullptr && fe != nullptr, "%s: null handle", who);
+  KWS_REQUIRE(B >= 0, "%s: negative batch", who);
   if (B == 0) return KWS_OK;
   const int T = kws_frontend_n_frames(fe, n_samples);
   const int F = kws_frontend_n_mels(fe);
   const size_t need = kws_model_wave_workspace_bytes(m, fe, B, n_samples, precision);
   if (need == 0 || workspace == nullptr || workspace_bytes < need) {
-    set_error("kws_model_forward_wave needs %zu bytes of workspace, got %zu", need, workspace_bytes);
+    set_error("%s needs %zu bytes of workspace, got %zu", who, need, workspace_bytes);
     return KWS_ERR_WORKSPACE;
   }
   // the model's scratch comes FIRST: its address (which the whole-network kernels' cached tensor maps are keyed on)
@@ -550,10 +556,25 @@ extern "C" int kws_model_forward_wave(kws_model_t* m, const kws_frontend_t* fe, 
   const size_t feat_bytes = round_up<size_t>((size_t)B * T * F * sizeof(float), 256);
   const size_t model_bytes = need - feat_bytes;
   float* feat = reinterpret_cast<float*>(static_cast<char*>(workspace) + model_bytes);
-  KWS_TRY(kws_mfcc_forward(fe, wav, B, n_samples, feat, stream));
+  if constexpr (sizeof(SMP) == 4) KWS_TRY(kws_mfcc_forward(fe, wav, B, n_samples, feat, stream));
+  else KWS_TRY(kws_mfcc_forward_pcm16(fe, wav, B, n_samples, feat, stream));
   int st = kws_model_forward(m, feat, B, T, F, logits, precision, workspace, model_bytes, stream);
   m->last_launches += 1;
   return st;
+}
+
+extern "C" int kws_model_forward_wave(kws_model_t* m, const kws_frontend_t* fe, const float* wav, int64_t B,
+                                      int n_samples, float* logits, int precision, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  return model_forward_wave_any<float>("kws_model_forward_wave", m, fe, wav, B, n_samples, logits, precision, workspace,
+                                       workspace_bytes, stream);
+}
+
+extern "C" int kws_model_forward_wave_pcm16(kws_model_t* m, const kws_frontend_t* fe, const int16_t* wav, int64_t B,
+                                            int n_samples, float* logits, int precision, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  return model_forward_wave_any<int16_t>("kws_model_forward_wave_pcm16", m, fe, wav, B, n_samples, logits, precision,
+                                         workspace, workspace_bytes, stream);
 }
 
 extern "C" int64_t kws_model_last_launches(const kws_model_t* m) { return m ? m->last_launches : 0; }

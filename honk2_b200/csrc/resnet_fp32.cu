@@ -5,6 +5,8 @@
 //   conv0_f32_kernel    conv_0 + ReLU + AvgPool          /root/reference/model/resnet.py:40-44
 //   conv3x3_f32_kernel  conv_i + ReLU + skip + BatchNorm /root/reference/model/resnet.py:48-55
 //   tail_f32_kernel     mean over H*W + Linear           /root/reference/model/resnet.py:57-59
+#include <algorithm>
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace kws {
@@ -285,13 +287,277 @@ conv3x3_f32_kernel(Conv3x3F32 a, Conv3x3Geom g) {
   }
 }
 
+
+// =============================================================================================
+// conv_i, resident-weight form (the default wherever it fits): same thread tile (8 rows x Q maps, lanes along w), but
+//   * the CTA is persistent (one per SM) and keeps the WHOLE layer's packed weights in shared memory -- they are read
+//     from global memory once per CTA instead of once per 8-row tile;
+//   * a CTA works on NS independent 8-row "units" (utterance, row group) at a time -- units are numbered through the
+//     whole sub-batch, so the last row group of one utterance and the first of the next share a CTA and no lane idles
+//     on the H = 101 -> 13 x 8 split;
+//   * the input rows of the next CK input maps arrive by cp.async (zero fill for rows / maps / units outside the
+//     problem = the reference's zero padding, resnet.py:22-24) into the other half of a double buffer while the
+//     FMAs of the current chunk run, continuously across units: the old kernel staged with dependent scalar loads
+//     between two __syncthreads and spent most of its time waiting for them (ncu: FMA pipe 20 %).
+// The left / right padding columns of every staged row are zeroed once and never written.
+// 13 warps: two 200-thread units of a 45-map, 40-column layer (128 registers: Q <= 9 fits without spills); the wider
+// thread tiles get 12 warps and up to 168 registers
+__host__ __device__ constexpr int res_max_threads(int Q) { return Q <= 9 ? 416 : 384; }
+
+struct ConvResGeom {
+  int Q, CG, NS, CK, n_chunks, wpad, row_stride, threads, sub_threads, units_per_utt, vec, seg_per_row;
+  int w_floats, sub_floats, buf_floats;   // packed weights; one unit's chunk [CK][3][8][row_stride]; NS of them
+  int64_t n_units, n_items;
+  uint32_t m_seg, m_24, m_ck, m_upu;      // magic multipliers: n / d == __umulhi(n, m) for the ranges used here
+  size_t smem;
+};
+
+static uint32_t magic_div(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ull + d - 1) / d); }
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t m) { return m == 0u ? n : __umulhi(n, m); }
+
+static bool conv3x3_res_geom(int64_t B, int C, int H, int W, int d, ConvResGeom* g) {
+  g->Q = conv3x3_f32_q(C);
+  g->CG = ceil_div(C, g->Q);
+  g->sub_threads = g->CG * W;
+  const int max_threads = res_max_threads(g->Q);
+  if (g->sub_threads > max_threads) return false;
+  g->units_per_utt = ceil_div(H, kPH);
+  g->n_units = B * (int64_t)g->units_per_utt;
+  if (g->n_units >= (1ll << 24)) return false;          // (fast_div exactness: n * d < 2^32)
+  g->wpad = d < W ? round_up(d, 4) : 0;
+  if (W == 40 && d <= 16) g->wpad = 16;   // the 40-mel maps: one compile-time row pitch (72 floats) for every dilation
+  g->row_stride = W + 2 * g->wpad;
+  g->vec = (W % 4 == 0) ? 1 : 0;
+  g->seg_per_row = g->vec ? W / 4 : W;
+  g->w_floats = C * 9 * g->CG * kQP;
+  const size_t cap = 226 * 1024;
+  int ns = max_threads / g->sub_threads;
+  if (ns > 8) ns = 8;
+  if ((int64_t)ns > g->n_units) ns = (int)g->n_units;
+  for (; ns >= 1; --ns) {
+    for (int ck = 8; ck >= 2; --ck) {
+      if (ck > C && ck > 2) continue;
+      const size_t need = sizeof(float) * ((size_t)g->w_floats + 2ull * ns * ck * 3 * kPH * g->row_stride);
+      if (need <= cap) {
+        g->NS = ns;
+        // even split of C over the chunks
+        const int chunks = ceil_div(C, ck);
+        g->CK = ceil_div(C, chunks);
+        g->n_chunks = chunks;
+        g->sub_floats = g->CK * 3 * kPH * g->row_stride;
+        g->buf_floats = ns * g->sub_floats;
+        g->smem = sizeof(float) * ((size_t)g->w_floats + 2ull * g->buf_floats);
+        g->threads = round_up(ns * g->sub_threads, 32);
+        g->n_items = ceil_div(g->n_units, (int64_t)ns);
+        g->m_seg = magic_div((uint32_t)g->seg_per_row);
+        g->m_24 = magic_div(3 * kPH);
+        g->m_ck = magic_div((uint32_t)g->CK);
+        g->m_upu = magic_div((uint32_t)g->units_per_utt);
+        // fast_div is exact while n * d < 2^32: pieces per chunk and unit numbers are far below that
+        return (int64_t)ns * g->CK * 3 * kPH * g->seg_per_row < (1 << 20);
+      }
+    }
+  }
+  return false;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// STRIDE > 0: the staged rows' pitch is known at compile time (row offsets become immediates of the loads; with a
+// runtime pitch every shared-memory load of the inner loop carried its own address instruction)
+// (13 warps = 4 on one of the SM's four sub-partitions of 16 K registers: 128 registers per thread; 12 warps: 168)
+template <int Q, int STRIDE>
+__global__ void __launch_bounds__(res_max_threads(Q), 1)
+conv3x3_f32_res_kernel(const Conv3x3F32 a, const ConvResGeom g) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_w = smem;                      // [C][9][CG*12]
+  float* s_in = smem + g.w_floats;        // [2][NS][CK][3 dh][8 rows][row_stride]
+  const int C = a.C, H = a.H, W = a.W, d = a.d;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int stride = STRIDE > 0 ? STRIDE : g.row_stride;
+
+  // ---- once per CTA: weights, zeroed staging buffers
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.wt);
+    float4* dst = reinterpret_cast<float4*>(s_w);
+    for (int i = tid; i < g.w_floats / 4; i += nthr) dst[i] = __ldg(src + i);
+    float4* z = reinterpret_cast<float4*>(s_in);
+    for (int i = tid; i < g.buf_floats / 2; i += nthr) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+
+  // ---- this thread's output tile: unit `sub` of the item, maps cg*Q .. cg*Q+Q-1, column w, 8 rows
+  const int sub = tid / g.sub_threads;
+  const int rem = tid - sub * g.sub_threads;
+  const int cg = rem / W;
+  const int w = rem - cg * W;
+  const bool active = sub < g.NS;
+  const bool side_taps = g.wpad > 0;   // d >= W: the dw != 0 taps only ever read padding
+
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  const int64_t n_my = first < g.n_items ? (g.n_items - first + step - 1) / step : 0;
+  const int n_chunks = g.n_chunks;
+  const int n_pieces = g.NS * g.CK * 3 * kPH * g.seg_per_row;
+  const uint32_t s_in_u32 = (uint32_t)__cvta_generic_to_shared(s_in);
+
+  // stage chunk `chunk` of item `item` into buffer `buf` (asynchronously)
+  auto stage = [&](int64_t item, int chunk, int buf) {
+    const int c0 = chunk * g.CK;
+    const uint32_t unit0 = (uint32_t)(item * g.NS);
+    for (int p = tid; p < n_pieces; p += nthr) {
+      const uint32_t rowid = fast_div((uint32_t)p, g.m_seg);
+      const uint32_t seg = (uint32_t)p - rowid * (uint32_t)g.seg_per_row;
+      const uint32_t sc = fast_div(rowid, g.m_24);
+      const uint32_t r24 = rowid - sc * (3u * kPH);
+      const uint32_t su = fast_div(sc, g.m_ck);
+      const uint32_t ci = sc - su * (uint32_t)g.CK;
+      const uint32_t unit = unit0 + su;
+      const uint32_t b = fast_div(unit, g.m_upu);
+      const int t = (int)(unit - b * (uint32_t)g.units_per_utt);
+      const int dh = (int)(r24 >> 3), r = (int)(r24 & 7u);
+      const int h = t * kPH + r + (dh - 1) * d;
+      const int c = c0 + (int)ci;
+      const bool ok = (int64_t)unit < g.n_units && c < C && h >= 0 && h < H;
+      const uint32_t dst = s_in_u32 + 4u * ((uint32_t)buf * (uint32_t)g.buf_floats + sc * (uint32_t)(3 * kPH * stride) +
+                                            r24 * (uint32_t)stride + (uint32_t)g.wpad + seg * (g.vec ? 4u : 1u));
+      const float* src = ok ? a.x + (((int64_t)b * C + c) * H + h) * (int64_t)W + seg * (g.vec ? 4 : 1) : a.x;
+      if (g.vec) cp_async16(dst, src, ok ? 16u : 0u);
+      else cp_async4(dst, src, ok ? 4u : 0u);
+    }
+    cp_async_commit();
+  };
+
+  float acc[kPH][Q];
+#pragma unroll
+  for (int j = 0; j < kPH; ++j)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[j][q] = 0.f;
+
+  if (n_my > 0) stage(first, 0, 0);
+  int64_t it_s = 0; int ch_s = 1;            // next (item index, chunk) to stage
+  if (ch_s == n_chunks) { ch_s = 0; ++it_s; }
+  int buf = 0;
+  for (int64_t it = 0; it < n_my; ++it) {
+    const int64_t item = first + it * step;
+    for (int ch = 0; ch < n_chunks; ++ch, buf ^= 1) {
+      if (it_s < n_my) {
+        stage(first + it_s * step, ch_s, buf ^ 1);
+        if (++ch_s == n_chunks) { ch_s = 0; ++it_s; }
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      if (active) {
+        const float* in_base = s_in + buf * g.buf_floats + sub * g.sub_floats + g.wpad + w;
+        const float* w_base = s_w + ((size_t)(ch * g.CK) * 9 * g.CG + cg) * kQP;
+        const int ck_n = min(g.CK, C - ch * g.CK);
+        for (int ci = 0; ci < ck_n; ++ci) {
+#pragma unroll
+          for (int dh = 0; dh < 3; ++dh) {
+            const float* in_row = in_base + ((ci * 3 + dh) * kPH) * stride;
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) {
+              if (dw != 1 && !side_taps) continue;
+              const float* ip = in_row + (dw - 1) * d;
+              float xv[kPH];
+#pragma unroll
+              for (int j = 0; j < kPH; ++j) xv[j] = ip[j * stride];
+              const float* wp = w_base + (size_t)((ci * 9 + dh * 3 + dw) * g.CG) * kQP;
+              float wv[kQP];
+#pragma unroll
+              for (int q4 = 0; q4 < kQP / 4; ++q4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(wp + 4 * q4);
+                wv[4 * q4] = t4.x; wv[4 * q4 + 1] = t4.y; wv[4 * q4 + 2] = t4.z; wv[4 * q4 + 3] = t4.w;
+              }
+#pragma unroll
+              for (int j = 0; j < kPH; ++j)
+#pragma unroll
+                for (int q = 0; q < Q; ++q) acc[j][q] = fmaf(xv[j], wv[q], acc[j][q]);
+            }
+          }
+        }
+      }
+      __syncthreads();   // buffer `buf` is refilled by the next iteration's stage()
+    }
+    // ---- epilogue of this item: ReLU, residual (pre-BN skip), BatchNorm (resnet.py:49-55)
+    if (active) {
+      const int64_t unit = item * g.NS + sub;
+      if (unit < g.n_units) {
+        const int64_t b = unit / g.units_per_utt;
+        const int h0 = (int)(unit - b * g.units_per_utt) * kPH;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const int co = cg * Q + q;
+          if (co < C) {
+            const float sc = __ldg(a.bn_scale + co), sh = __ldg(a.bn_shift + co);
+            const int64_t off0 = ((b * C + co) * (int64_t)H + h0) * W + w;
+            float v[kPH];
+#pragma unroll
+            for (int j = 0; j < kPH; ++j) v[j] = fmaxf(acc[j][q], 0.f);
+            if (a.prev_in) {
+#pragma unroll
+              for (int j = 0; j < kPH; ++j) if (h0 + j < H) v[j] += a.prev_in[off0 + (int64_t)j * W];
+#pragma unroll
+              for (int j = 0; j < kPH; ++j) if (h0 + j < H) a.prev_out[off0 + (int64_t)j * W] = v[j];
+            }
+#pragma unroll
+            for (int j = 0; j < kPH; ++j) if (h0 + j < H) a.y[off0 + (int64_t)j * W] = fmaf(v[j], sc, sh);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kPH; ++j)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) acc[j][q] = 0.f;
+  }
+}
+
 int launch_conv3x3_f32(const Conv3x3F32& a, cudaStream_t st) {
-  Conv3x3Geom g;
   KWS_REQUIRE(a.C >= 1 && a.H >= 1 && a.W >= 1 && a.d >= 1, "conv3x3: bad shape");
+  KWS_REQUIRE((a.prev_in == nullptr) == (a.prev_out == nullptr), "conv3x3: prev_in/prev_out mismatch");
+  ConvResGeom rg;
+  if (a.resident && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && conv3x3_res_geom(a.B, a.C, a.H, a.W, a.d, &rg)) {
+    const unsigned grid = (unsigned)std::min<int64_t>(rg.n_items, kNumSMs);
+#define KWS_LAUNCH_C3R(Q_)                                                                        \
+  case Q_:                                                                                        \
+    if (rg.row_stride == 72) {                                                                    \
+      KWS_CUDA(cudaFuncSetAttribute(conv3x3_f32_res_kernel<Q_, 72>,                               \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));    \
+      conv3x3_f32_res_kernel<Q_, 72><<<grid, rg.threads, rg.smem, st>>>(a, rg);                   \
+    } else {                                                                                      \
+      KWS_CUDA(cudaFuncSetAttribute(conv3x3_f32_res_kernel<Q_, 0>,                                \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));    \
+      conv3x3_f32_res_kernel<Q_, 0><<<grid, rg.threads, rg.smem, st>>>(a, rg);                    \
+    }                                                                                             \
+    break;
+    switch (rg.Q) {
+      KWS_LAUNCH_C3R(8)
+      KWS_LAUNCH_C3R(9)
+      KWS_LAUNCH_C3R(10)
+      KWS_LAUNCH_C3R(11)
+      KWS_LAUNCH_C3R(12)
+      default:
+        set_error("conv3x3: no kernel for Q=%d", rg.Q);
+        return KWS_ERR_INVALID;
+    }
+#undef KWS_LAUNCH_C3R
+    KWS_CHECK_LAUNCH();
+    return KWS_OK;
+  }
+  Conv3x3Geom g;
   KWS_REQUIRE(conv3x3_geom(a.C, a.H, a.W, a.d, &g),
               "conv3x3 fp32: unsupported geometry C=%d H=%d W=%d d=%d", a.C, a.H, a.W, a.d);
   KWS_REQUIRE(a.B <= 65535, "conv3x3: chunk too large");
-  KWS_REQUIRE((a.prev_in == nullptr) == (a.prev_out == nullptr), "conv3x3: prev_in/prev_out mismatch");
   dim3 grid(g.tiles_h, (unsigned)a.B);
 #define KWS_LAUNCH_C3(Q_)                                                                        \
   case Q_:                                                                                       \

@@ -74,12 +74,15 @@ class HostPipeline(object):
     returning).  Calls may be issued back to back without synchronising: a staging slot is only refilled after the
     forward that read it has finished (``consumed`` events, also across calls)."""
 
-    def __init__(self, model, audio_processor, n_samples, sub_batch=2048, device=None, slots=3):
+    def __init__(self, model, audio_processor, n_samples, sub_batch=2048, device=None, slots=3, dtype=torch.float32):
         self.model, self.ap = model, audio_processor
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.sub = int(sub_batch)
         self.slots = max(2, int(slots))
-        self.stage = [torch.empty((self.sub, n_samples), dtype=torch.float32, device=self.device)
+        if dtype not in (torch.float32, torch.int16):
+            raise ValueError("HostPipeline stages float32 waveforms or int16 PCM samples")
+        self.dtype = dtype   # int16: 16-bit PCM as in the wav files -- half the host->device bytes, identical logits
+        self.stage = [torch.empty((self.sub, n_samples), dtype=dtype, device=self.device)
                       for _ in range(self.slots)]
         self.dev_logits = [torch.empty((self.sub, model.n_labels), dtype=torch.float32, device=self.device)
                            for _ in range(self.slots)]
@@ -90,6 +93,8 @@ class HostPipeline(object):
 
     def __call__(self, host_waves, host_logits, sync=True):
         n = host_waves.shape[0]
+        if host_waves.dtype != self.dtype:
+            raise ValueError(f"this pipeline stages {self.dtype} waveforms, got {host_waves.dtype}")
         main = torch.cuda.current_stream(self.device)
         spans = [(b0, min(n, b0 + self.sub)) for b0 in range(0, n, self.sub)]
         done = torch.cuda.Event()

@@ -93,7 +93,7 @@ class BaseModel(nn.Module):
             raise ValueError(f"precision must be one of {sorted(_native.PRECISIONS)}, got {self.precision!r}")
         return _native.PRECISIONS[self.precision]
 
-    def _check_input(self, x, dims):
+    def _check_input(self, x, dims, pcm16_ok=False):
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise _native.NativeError("honk2_b200 models run on a B200 only: move the input (and the model) "
                                       "to a CUDA device; there is no CPU fallback")
@@ -102,7 +102,7 @@ class BaseModel(nn.Module):
                                       "(run/test.py:21)")
         if x.dim() != dims:
             raise ValueError(f"expected a {dims}-D input, got shape {tuple(x.shape)}")
-        if x.dtype != torch.float32:
+        if x.dtype != torch.float32 and not (pcm16_ok and x.dtype == torch.int16):
             x = x.float()
         return x.contiguous()
 
@@ -136,8 +136,11 @@ class BaseModel(nn.Module):
 
     def forward_wave(self, waves, audio_processor, out=None):
         """Fused collate + forward: CUDA float32 waveforms [B, N] -> logits [B, n_labels]
-        (data_loader/audio_data_loader.py:26-29 followed by model(x)).  `out`: optional preallocated logits."""
-        waves = self._check_input(waves, 2)
+        (data_loader/audio_data_loader.py:26-29 followed by model(x)).  `out`: optional preallocated logits.
+        int16 waveforms are 16-bit PCM samples (see AudioProcessor.compute_mfccs_batch): same logits, bit for bit, as
+        for waves.float() / 32768."""
+        waves = self._check_input(waves, 2, pcm16_ok=True)
+        pcm16 = waves.dtype == torch.int16
         B, N = waves.shape
         lib, st = self._state(waves.device)
         fe = audio_processor._frontend(waves.device)
@@ -150,10 +153,12 @@ class BaseModel(nn.Module):
             if need == 0:
                 raise _native.NativeError(f"{type(self).__name__}: precision {self.precision!r} is not available")
             ws = self._workspace(st, need, waves.device)
-            _native.check(lib.kws_model_forward_wave(
+            fn = lib.kws_model_forward_wave_pcm16 if pcm16 else lib.kws_model_forward_wave
+            _native.check(fn(
                 st["handle"], fe, C.c_void_p(waves.data_ptr()), B, N, C.c_void_p(logits.data_ptr()), prec,
                 C.c_void_p(ws.data_ptr()), ws.numel(),
-                C.c_void_p(torch.cuda.current_stream(waves.device).cuda_stream)), "kws_model_forward_wave")
+                C.c_void_p(torch.cuda.current_stream(waves.device).cuda_stream)),
+                "kws_model_forward_wave_pcm16" if pcm16 else "kws_model_forward_wave")
         return logits
 
     def last_launches(self, device=None):

@@ -62,6 +62,12 @@ int kws_frontend_n_frames(const kws_frontend_t* fe, int n_samples);
 int kws_frontend_n_mels(const kws_frontend_t* fe);
 int kws_mfcc_forward(const kws_frontend_t* fe, const float* wav, int64_t B, int n_samples,
                      float* feat, void* stream);
+/* The same front-end on the 16-bit PCM samples of the wav files the reference's datasets read
+ * (dataset/dataset_utils.py:20,51 -> librosa.core.load, which returns float32(s / 32768) for a 16-bit file): wav
+ * [B, n_samples] int16.  The conversion happens while the samples are staged, so feat is bit-identical to
+ * kws_mfcc_forward on the converted floats; host->device and HBM traffic of the waveforms halve. */
+int kws_mfcc_forward_pcm16(const kws_frontend_t* fe, const int16_t* wav, int64_t B, int n_samples,
+                           float* feat, void* stream);
 /* Streaming-window front-end: replaces StreamingDataset.__getitem__'s window slicing
  * (dataset/dataset_utils.py:28-31,72 -- window k = stream[k*shift : k*shift + window]) followed by the per-window
  * compute_mfccs of collate_fn (audio_data_loader.py:26-29).  wav points at the first sample of the first window and
@@ -137,6 +143,10 @@ size_t kws_model_wave_workspace_bytes(const kws_model_t* m, const kws_frontend_t
 int kws_model_forward_wave(kws_model_t* m, const kws_frontend_t* fe, const float* wav, int64_t B,
                            int n_samples, float* logits, int precision, void* workspace,
                            size_t workspace_bytes, void* stream);
+/* kws_model_forward_wave on int16 PCM waveforms (see kws_mfcc_forward_pcm16); same workspace. */
+int kws_model_forward_wave_pcm16(kws_model_t* m, const kws_frontend_t* fe, const int16_t* wav, int64_t B,
+                                 int n_samples, float* logits, int precision, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 /* Number of kernel launches the last forward on this handle issued (bench "gpu_launches"). */
 int64_t kws_model_last_launches(const kws_model_t* m);
 /* Name of the kernel family a forward of a [B][T][F] batch runs in the given precision (bench / profile labels):

@@ -510,6 +510,45 @@ def test_host_pipeline_back_to_back_calls(dev):
     assert torch.equal(oc, oa)
 
 
+@pytest.mark.parametrize("n", [16000, 15999, 8000, 4007, 144000])
+def test_pcm16_waveforms_give_bit_identical_features(dev, n):
+    """16-bit PCM input (the wav files' own format; librosa hands the reference float32(s / 32768)): the front-end converts
+    while staging, so features and logits equal those of the converted floats bit for bit -- odd lengths take the
+    unaligned staging path, full-scale samples included."""
+    rng = np.random.default_rng(n)
+    pcm = rng.integers(-32768, 32768, size=(9, n), dtype=np.int16)
+    pcm[0, :8] = [-32768, 32767, 0, 1, -1, 12345, -12345, 7]
+    ap = AudioProcessor()
+    w16 = torch.from_numpy(pcm).to(dev)
+    wf = torch.from_numpy(pcm.astype(np.float32) / 32768.0).to(dev)
+    f16, ff = ap.compute_mfccs_batch(w16), ap.compute_mfccs_batch(wf)
+    assert f16.dtype == torch.float32 and torch.equal(f16, ff)
+    # ... and against the oracle on the converted floats
+    ref = mfcc_ref.compute_mfccs_batch(pcm[:2].astype(np.float32) / 32768.0)
+    assert mfcc_err(f16[:2].cpu().numpy(), ref)[0] <= MFCC_TOL
+    if n == 16000:
+        m, _ = gpu_model("res8", "hardened", dev)
+        with torch.no_grad():
+            assert torch.equal(m.forward_wave(w16, ap), m.forward_wave(wf, ap))
+
+
+def test_host_pipeline_pcm16(dev):
+    from honk2_b200.evaluate import HostPipeline
+    ap = AudioProcessor()
+    m, _ = gpu_model("res8", "hardened", dev)
+    n, sub = 300, 128
+    pcm = np.round(synth.broadband(n, seed=4) * 20000).clip(-32768, 32767).astype(np.int16)
+    h16 = torch.from_numpy(pcm).pin_memory()
+    out = torch.empty((n, 12)).pin_memory()
+    pipe = HostPipeline(m, ap, 16000, sub_batch=sub, device=dev, dtype=torch.int16)
+    pipe(h16, out)
+    with torch.no_grad():
+        ref = m.forward_wave(torch.from_numpy(pcm.astype(np.float32) / 32768.0).to(dev), ap).cpu()
+    assert torch.equal(out, ref)
+    with pytest.raises(ValueError):
+        pipe(torch.zeros((4, 16000)).pin_memory(), out[:4])
+
+
 def test_audio_data_loader_yields_feature_batches(dev):
     """data_loader.AudioDataLoader (audio_data_loader.py:10-35): (FloatTensor[B, T, 40], LongTensor[B]) batches."""
     from honk2_b200.data_loader import AudioDataLoader
@@ -522,6 +561,28 @@ def test_audio_data_loader_yields_feature_batches(dev):
     ref = mfcc_ref.compute_mfccs_batch(waves)
     err, _, ok = mfcc_err(torch.cat([x for x, _ in got]).cpu().numpy(), ref)
     assert err <= MFCC_TOL and ok
+
+
+@pytest.mark.parametrize("name", ["res15", "res8", "res26_narrow"])
+def test_fp32_resident_weight_kernel_matches_tile_kernel(dev, monkeypatch, name, model_golden):
+    """The fp32 C -> C layers run on the persistent resident-weight kernel (conv3x3_f32_res_kernel: cp.async double
+    buffer, units numbered through the sub-batch); HONK2_F32_RESIDENT=0 selects the older one-tile-per-CTA kernel.  Same
+    thread tile and the same order of the fp32 additions, so the logits must be bit-identical -- on a ragged batch that
+    leaves the last work item of the persistent kernel half empty."""
+    monkeypatch.setenv("HONK2_F32_RESIDENT", "0")
+    m_tile, sd = gpu_model(name, "hardened", dev)
+    monkeypatch.setenv("HONK2_F32_RESIDENT", "1")
+    m_res, _ = gpu_model(name, "hardened", dev)
+    feats = mfcc_ref.compute_mfccs_batch(synth.noisy_dataset_like(37, seed=21))
+    x = torch.from_numpy(feats).to(dev)
+    with torch.no_grad():
+        y_tile, y_res = m_tile(x), m_res(x)
+        y_long = m_res(torch.from_numpy(model_golden["feats_long"]).to(dev)).cpu().numpy()
+    assert torch.equal(y_tile, y_res)
+    kind, cfg = model_config(name)
+    ref = model_ref.forward(kind, sd, cfg, torch.from_numpy(feats)).numpy()
+    assert logit_err(y_res.cpu().numpy(), ref) <= LOGIT_TOL
+    assert logit_err(y_long, model_golden[f"{name}/hardened/logits_long"]) <= LOGIT_TOL
 
 
 def test_bf16_column_sweep_kernel_matches_position_major_kernel_at_full_batch(dev, monkeypatch):

@@ -95,3 +95,22 @@ def test_against_torchaudio(golden_waves):
         assert scaled_err(ta[live], ours[live]) < 1e-4, name
     fb = torchaudio.functional.melscale_fbanks(241, 20.0, 4000.0, 40, 16000, norm="slaney", mel_scale="slaney")
     assert np.abs(fb.numpy().T - mfcc_ref.mel_filterbank()).max() < 1e-6
+
+
+def test_against_transformers_audio_utils(golden_waves):
+    """Second independent pin: `transformers.audio_utils` (its `spectrogram` / `mel_filter_bank` are, by their own
+    docstrings, adapted from librosa's stft / filters.mel -- the library the reference calls at
+    utils/audio_processor.py:19-26 and that cannot be installed here).  Same framing (center, reflect), periodic Hann,
+    power 2, Slaney scale + Slaney area normalisation; the restatement agrees to float32 rounding."""
+    au = pytest.importorskip("transformers.audio_utils")
+    fb = au.mel_filter_bank(241, 40, 20.0, 4000.0, 16000, norm="slaney", mel_scale="slaney")
+    assert np.abs(fb.T - mfcc_ref.mel_filterbank()).max() < 1e-7
+    win = au.window_function(480, "hann", periodic=True)
+    for name in ("broadband", "noisy", "speechlike"):
+        for y in golden_waves[name][:3].astype(np.float32):
+            sp = au.spectrogram(y, win, 480, 160, fft_length=480, power=2.0, center=True, pad_mode="reflect",
+                                mel_filters=fb, mel_floor=0.0)
+            ours = mfcc_ref.compute_mfccs(y)[..., 0]
+            live = ours != 0
+            ref = 2.0 * np.log(sp.T[live])
+            assert scaled_err(ours[live], ref) < 2e-6, name
