@@ -68,7 +68,7 @@ class AudioProcessor(object):
         """waves: CUDA float32 [B, N] (contiguous) -> CUDA float32 [B, T, n_mels].
 
         int16 waveforms are taken as 16-bit PCM, the samples of the wav files behind the reference's datasets
-        (librosa.core.load returns float32(s / 32768) for them, dataset/dataset_utils.py:20,51): the kernel converts while
+        (librosa.core.load returns float32(s / 32768) for them, dataset/gsc_dataset.py:169, hey_snips_dataset.py:74): the kernel converts while
         it stages, the features are bit-identical to those of the converted floats, and the waveforms cost half the
         host->device and HBM bytes."""
         if not (isinstance(waves, torch.Tensor) and waves.is_cuda):

@@ -16,7 +16,7 @@ int launch_conv0_f32(const float* feat, const float* w0, float* out, int64_t B, 
 // (resnet.py:48-55).  wt is the packed layout made by pack_conv3x3_f32 (model.cu).
 struct Conv3x3F32 {
   const float* x;        // [B][C][H][W] input (post-BN output of the previous layer)
-  const float* wt;       // [C][9][CG*12] zero padded
+  const float* wt;       // [C][9][CG*QP] zero padded (QP = Q rounded up to a multiple of 4)
   const float* prev_in;  // pre-BN skip tensor to add (even layers) or nullptr
   float* prev_out;       // where the new skip tensor goes (even layers; may alias prev_in)
   float* y;              // [B][C][H][W] BN output

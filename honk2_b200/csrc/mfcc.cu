@@ -130,7 +130,7 @@ __device__ __forceinline__ void dft15(const float2 (&y)[15], float2 (&z)[15]) {
 // (t = 0, 1, T-2, T-1); every other frame of a window is shared with the stream-level frame table.
 //
 // SMP = float: waveforms as the reference's loader hands them over (librosa float32 in [-1, 1)).  SMP = int16_t: the 16-bit
-// PCM samples as they sit in the wav files (dataset/dataset_utils.py loads them through librosa, which returns exactly
+// PCM samples as they sit in the wav files (dataset/gsc_dataset.py:169 loads them through librosa, which returns exactly
 // s / 32768): converted while staging, bit-identical features, half the bytes from the host and from HBM.
 __device__ __forceinline__ float smp_ld(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float smp_ld(const int16_t* p) { return (float)__ldg(p) * (1.f / 32768.f); }

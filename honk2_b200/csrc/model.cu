@@ -28,7 +28,7 @@ struct Model {
   float* blob = nullptr;  // one allocation
   size_t blob_bytes = 0;
   float* r_conv0 = nullptr;               // [C][9]
-  std::vector<float*> r_conv;             // [n][C][9][CG*12]
+  std::vector<float*> r_conv;             // [n][C][9][CG*QP]
   std::vector<float*> r_bn_scale, r_bn_shift;  // [n][C]
   float* r_out_w = nullptr;               // [L][C]
   float* r_out_b = nullptr;               // [L]
@@ -49,13 +49,14 @@ static int resnet_dilation(const kws_resnet_config& c, int i) {
 // ---------------------------------------------------------------------------------------------
 // packing kernels (run once per load_state_dict)
 
-// torch [Cout][Cin][3][3] -> [Cin][9][CG*12], zero padded
+// torch [Cout][Cin][3][3] -> [Cin][9][CG*QP], zero padded (QP = Q rounded up to a multiple of 4)
 __global__ void pack_conv3x3_f32_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int Q,
                                         int CG) {
-  const int total = C * 9 * CG * 12;
+  const int QP = (Q + 3) & ~3;
+  const int total = C * 9 * CG * QP;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int q = i % 12;
-    int t = i / 12;
+    const int q = i % QP;
+    int t = i / QP;
     const int cg = t % CG; t /= CG;
     const int tap = t % 9;
     const int ci = t / 9;
@@ -128,7 +129,7 @@ extern "C" int kws_resnet_create(const kws_resnet_config* cfg, kws_model_t** out
   const size_t o_conv0 = bp.take((size_t)C * 9);
   std::vector<size_t> o_conv(n), o_sc(n), o_sh(n);
   for (int i = 0; i < n; ++i) {
-    o_conv[i] = bp.take((size_t)C * 9 * CG * 12);
+    o_conv[i] = bp.take((size_t)C * 9 * CG * ((Q + 3) & ~3));
     o_sc[i] = bp.take(C);
     o_sh[i] = bp.take(C);
   }
@@ -172,7 +173,7 @@ extern "C" int kws_resnet_set_weights(kws_model_t* m, const kws_resnet_weights* 
   for (int i = 0; i < n; ++i) {
     KWS_REQUIRE(w->conv_w[i] && w->bn_mean[i] && w->bn_var[i], "kws_resnet_set_weights: layer %d has a null tensor",
                 i + 1);
-    pack_conv3x3_f32_kernel<<<ceil_div(C * 9 * CG * 12, 256), 256, 0, st>>>(w->conv_w[i], m->r_conv[i], C, Q, CG);
+    pack_conv3x3_f32_kernel<<<ceil_div(C * 9 * CG * ((Q + 3) & ~3), 256), 256, 0, st>>>(w->conv_w[i], m->r_conv[i], C, Q, CG);
     KWS_CUDA(cudaGetLastError());
     pack_bn_kernel<<<ceil_div(C, 128), 128, 0, st>>>(w->bn_mean[i], w->bn_var[i], m->r_bn_scale[i],
                                                     m->r_bn_shift[i], C, kBnEps);

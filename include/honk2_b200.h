@@ -63,7 +63,7 @@ int kws_frontend_n_mels(const kws_frontend_t* fe);
 int kws_mfcc_forward(const kws_frontend_t* fe, const float* wav, int64_t B, int n_samples,
                      float* feat, void* stream);
 /* The same front-end on the 16-bit PCM samples of the wav files the reference's datasets read
- * (dataset/dataset_utils.py:20,51 -> librosa.core.load, which returns float32(s / 32768) for a 16-bit file): wav
+ * (dataset/gsc_dataset.py:169, dataset/hey_snips_dataset.py:74 -> librosa.core.load, which returns float32(s / 32768) for a 16-bit file): wav
  * [B, n_samples] int16.  The conversion happens while the samples are staged, so feat is bit-identical to
  * kws_mfcc_forward on the converted floats; host->device and HBM traffic of the waveforms halve. */
 int kws_mfcc_forward_pcm16(const kws_frontend_t* fe, const int16_t* wav, int64_t B, int n_samples,
