@@ -51,6 +51,15 @@ FLOPS_PER_UTT = {  # SURVEY.md section 8d / BASELINE.md section 3 (2*MAC, padded
 }
 
 
+DATA = "synthetic (broadband noise clips rounded to 16-bit PCM, s / 32768: what librosa hands the reference for a 16-bit wav)"
+
+
+def pcm_round(w):
+    """float32 clips -> the nearest 16-bit PCM clips, still as float32 (s / 32768, exact).  Both arms, the fp32 and the
+    int16 e2e paths then process IDENTICAL samples."""
+    return (np.clip(np.round(w * 32768.0), -32768, 32767) / 32768.0).astype(np.float32)
+
+
 def committed_traffic(kernel_path, batch, precision):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same command
     (profiles/*traffic*.json; the newest record whose kernel, precision and batch match), or None."""
@@ -153,7 +162,7 @@ def run_reference_arm(args):
     ref = bench_ref.CpuReference(args.model)
     batch = args.ref_batch
     # the synthetic waveforms are made BEFORE the timed region (the GPU arm's are resident before its region too)
-    waves = [bench_ref.broadband(batch, N=N_SAMPLES, seed=1000 + i) for i in range(args.warmup + args.steps)]
+    waves = [pcm_round(bench_ref.broadband(batch, N=N_SAMPLES, seed=1000 + i)) for i in range(args.warmup + args.steps)]
     for i in range(args.warmup):
         ref.step(waves[i])
     t_fe = t_model = 0.0
@@ -168,7 +177,7 @@ def run_reference_arm(args):
               f"sample + PyTorch-CPU fp32 restatement of {args.model} forward; front-end {t_fe:.2f} s, model {t_model:.2f} s")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA,
             # the SAME workload as the GPU arm (its `config`); `sample_per_step` is what one timed step of this arm covers
             "config": dict(workload_config(args, args.batch), sample_per_step=batch),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": sample},
@@ -285,7 +294,7 @@ def main():
 
     # synthetic data: two distinct batches (each 524 MB > L2), device resident for `value`
     n_sets = 2
-    host_sets = [torch.from_numpy(synth.broadband(B_cfg, N=N_SAMPLES, seed=100 * rank + s)).pin_memory() for s in range(n_sets)]
+    host_sets = [torch.from_numpy(pcm_round(synth.broadband(B_cfg, N=N_SAMPLES, seed=100 * rank + s))).pin_memory() for s in range(n_sets)]
     host_f32 = host_sets
     dev_sets = [h.to(dev) for h in host_sets]
     targets = torch.randint(0, model.n_labels, (B_cfg,), device=dev)
@@ -372,6 +381,10 @@ def main():
         # datasets (librosa returns float32(s / 32768) for them): half the host->device bytes, bit-identical logits
         host_pcm = [(h * 32768.0).round().clamp(-32768, 32767).to(torch.int16).pin_memory() for h in host_f32]
         ms_e2e_pcm = timed_e2e(B, K, hosts=host_pcm)
+        # (the clips are 16-bit PCM already, see pcm_round: the two paths must agree bit for bit)
+        n_chk = min(B, 1024)
+        pcm_same = bool(torch.equal(model.forward_wave(host_pcm[0][:n_chk].to(dev), fe),
+                                    model.forward_wave(dev_sets[0][:n_chk], fe)))
         del host_pcm
 
         strong = None
@@ -484,10 +497,10 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         from oracle import bench_ref
         ref = bench_ref.CpuReference(args.model)
-        ref.step(bench_ref.broadband(8, N=N_SAMPLES, seed=1))
+        ref.step(pcm_round(bench_ref.broadband(8, N=N_SAMPLES, seed=1)))
         n, t_cpu, fe_s, mo_s = 0, 0.0, 0.0, 0.0
         while t_cpu < args.cpu_seconds and n < 64 * 64:
-            waves = bench_ref.broadband(args.ref_batch, N=N_SAMPLES, seed=3000 + n)
+            waves = pcm_round(bench_ref.broadband(args.ref_batch, N=N_SAMPLES, seed=3000 + n))
             t0 = time.perf_counter()
             a, b, _ = ref.step(waves)
             t_cpu += time.perf_counter() - t0
@@ -549,7 +562,7 @@ def main():
     dtype = {"bf16": "bf16", "bf16x3": "bf16 (split hi+lo pairs, 3 MMAs per product, fp32 accumulate)", "fp32": "f32"}[precision]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": dtype, "data": "synthetic",
+            "dtype": dtype, "data": DATA,
             "config": dict(workload_config(args, B), precision=precision, parallelism=f"dp{world}",
                            exchange="one all-gather of [logits | correct,total] per step" if world > 1 else "none",
                            e2e_pipeline=f"{args.e2e_slots} staging slots x {min(args.e2e_sub_batch, B)} clips"),
@@ -558,8 +571,9 @@ def main():
                     "d2h_bytes_per_step": B * model.n_labels * 4, "ms_per_step": ms_e2e / K},
             "e2e_pcm16": {"value": B * world * K / (ms_e2e_pcm / 1e3), "unit": UNIT, "h2d_bytes_per_step": B * N_SAMPLES * 2,
                           "d2h_bytes_per_step": B * model.n_labels * 4, "ms_per_step": ms_e2e_pcm / K,
-                          "note": "host waveforms as int16 PCM (the wav files' format) through kws_model_forward_wave_pcm16; "
-                                  "same synthetic clips rounded to 16 bits"},
+                          "logits_bit_identical_to_f32_path": pcm_same,
+                          "note": "the SAME clips handed over as int16 PCM host buffers (the wav files' sample format) through "
+                                  "kws_model_forward_wave_pcm16: half the host->device bytes"},
             "gpu_launches": launches, "roofline": roof, "frontend_roofline": fe_roof, "parity": par,
             "parity_mode": second, "cpu_baseline": cpu, "gpu_eager_bar": eager, "streaming_windows": streaming,
             "strong_scaling": strong, "numa": numa_info, "other_configs": others,
