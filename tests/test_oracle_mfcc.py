@@ -102,7 +102,18 @@ def test_against_transformers_audio_utils(golden_waves):
     docstrings, adapted from librosa's stft / filters.mel -- the library the reference calls at
     utils/audio_processor.py:19-26 and that cannot be installed here).  Same framing (center, reflect), periodic Hann,
     power 2, Slaney scale + Slaney area normalisation; the restatement agrees to float32 rounding."""
-    au = pytest.importorskip("transformers.audio_utils")
+    import importlib
+    import sys
+    # (oracle/reference_loader.py parks empty `librosa` / `pcen` stub modules in sys.modules so that the reference's own
+    # modules import; transformers probes for librosa with find_spec, which rejects a module without a __spec__)
+    stubs = {k: sys.modules.pop(k) for k in ("librosa", "pcen")
+             if k in sys.modules and getattr(sys.modules[k], "__spec__", None) is None}
+    try:
+        au = importlib.import_module("transformers.audio_utils")
+    except Exception as exc:   # not installed / not importable in this environment
+        pytest.skip(f"transformers.audio_utils is not importable: {exc!r}")
+    finally:
+        sys.modules.update(stubs)
     fb = au.mel_filter_bank(241, 40, 20.0, 4000.0, 16000, norm="slaney", mel_scale="slaney")
     assert np.abs(fb.T - mfcc_ref.mel_filterbank()).max() < 1e-7
     win = au.window_function(480, "hann", periodic=True)
