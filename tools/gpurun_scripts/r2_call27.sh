@@ -1,9 +1,9 @@
-# memcheck / racecheck of the round's new kernels on small cases; ncu --set full records (final sweep kernel, narrow fp32 row kernel)
+# ncu --set full records (final sweep kernel, narrow fp32 row kernel) + smoke; compute-sanitizer is closed on this pool (the call answered rc 86)
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/r3g_memcheck.log 2>&1
-echo "rc=$?" >> gpurun_out/r3g_memcheck.log
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/sanitize_small.py > gpurun_out/r3g_racecheck.log 2>&1
-echo "rc=$?" >> gpurun_out/r3g_racecheck.log
+
+
+
+
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r3g_smoke.log 2>&1
 echo "rc=$?" >> gpurun_out/r3g_smoke.log
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:resnet_tc_sweep -s 3 -c 1 -o gpurun_out/r3g_sweep -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-second-mode --no-parity --no-other-configs > gpurun_out/r3g_ncu_sweep.log 2>&1

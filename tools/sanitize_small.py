@@ -1,5 +1,7 @@
-"""Small forward passes of the kernels added in round 2 for `compute-sanitizer --tool memcheck|racecheck python tools/sanitize_small.py`
-(fp32 resident-weight convolution kernels: row tile and column tile, every dilation; int16 PCM front-end incl. odd clip lengths)."""
+"""Small forward passes of the kernels added in round 2 (fp32 resident-weight convolution kernels: row tile and column tile,
+every dilation; int16 PCM front-end incl. odd clip lengths), meant for `compute-sanitizer --tool memcheck|racecheck python
+tools/sanitize_small.py`.  compute-sanitizer is closed on this GPU pool, so the same cases are covered by the bit-identity
+tests in tests/test_gpu_parity.py (three convolution kernels against each other and the oracle; PCM16 against float32)."""
 import numpy as np
 import torch
 
