@@ -68,7 +68,9 @@ class BaseModel(nn.Module):
                 raise _native.NativeError(
                     f"model tensors live on {t.device} but the input is on {device}; call model.to(device)")
         stamp = self._stamp()
-        if st["stamp"] != stamp:   # first call, load_state_dict, .to(), or an in-place update
+        # A torch.nn.DataParallel replica (run/test.py:69-70) carries fresh broadcast copies of the weights on every call, and
+        # the caching allocator may hand them the addresses of the previous call's copies: always repack for a replica.
+        if st["stamp"] != stamp or getattr(self, "_is_replica", False):   # first call, load_state_dict, .to(), in-place update
             with torch.cuda.device(idx):
                 self._upload(lib, st["handle"], C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
                 # the contiguous fp32 staging copies made by _upload die when it returns
@@ -170,11 +172,16 @@ class BaseModel(nn.Module):
     def __del__(self):
         # (never dlopen from a destructor: a model that was only ever used on the CPU side -- state_dict, parameter
         # counts -- must not map the native library into its process)
+        # A torch.nn.DataParallel replica (run/test.py:69-70) is a shallow copy that SHARES this dict of handles with the
+        # module it was made from and dies after every forward: only the original owns (and frees) the handles.
+        if getattr(self, "_is_replica", False):
+            return
         try:
             lib = _native.loaded()
             if lib is not None:
                 for st in self._native_state.values():
                     lib.kws_model_destroy(st["handle"])
+                self._native_state.clear()
         except Exception:
             pass
 

@@ -549,6 +549,25 @@ def test_host_pipeline_pcm16(dev):
         pipe(torch.zeros((4, 16000)).pin_memory(), out[:4])
 
 
+def test_model_under_data_parallel(dev):
+    """run/test.py:69-70 wraps the model in torch.nn.DataParallel whenever the box has more than one GPU, so a drop-in
+    class has to survive replicate() (replicas carry their parameters as plain attributes, fresh copies every call) and
+    forward() from DataParallel's worker threads, one replica per device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    for name, precision in (("res15", "fp32"), ("res15", "bf16x3"), ("cnn-trad-fpool3", "fp32")):
+        m, sd = gpu_model(name, "hardened", dev, precision=precision)
+        feats = torch.from_numpy(mfcc_ref.compute_mfccs_batch(synth.noisy_dataset_like(11, seed=5))).to(dev)
+        dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+        with torch.no_grad():
+            y_dp = dp(feats)
+            y_dp2 = dp(feats)
+            y = m(feats)
+        assert y_dp.device == feats.device and y_dp.shape == y.shape
+        assert torch.equal(y_dp, y), (name, precision)
+        assert torch.equal(y_dp2, y)
+
+
 def test_audio_data_loader_yields_feature_batches(dev):
     """data_loader.AudioDataLoader (audio_data_loader.py:10-35): (FloatTensor[B, T, 40], LongTensor[B]) batches."""
     from honk2_b200.data_loader import AudioDataLoader
