@@ -604,6 +604,50 @@ def test_fp32_resident_weight_kernel_matches_tile_kernel(dev, monkeypatch, name,
     assert logit_err(y_long, model_golden[f"{name}/hardened/logits_long"]) <= LOGIT_TOL
 
 
+@pytest.mark.parametrize("C,n_layers,pool,T,F,B", [
+    (45, 13, None, 37, 24, 5),      # row kernel, 3 column blocks, ragged last unit (37 = 4 x 8 + 5), dilation up to 16
+    (30, 7, None, 64, 48, 3),       # 30 maps (Q = 10, 3 groups), 48 columns, dilation up to 4
+    (64, 4, None, 17, 16, 6),       # 64 maps (Q = 11, 6 groups: 165 KB of packed weights per layer)
+    (19, 10, None, 101, 8, 9),      # one column block
+    (45, 6, [2, 3], 50, 39, 7),     # pooled to 25 x 13: the column-tile resident kernel, no dilation key
+    (12, 16, None, 9, 40, 4),       # 12 maps, 9 rows (two units, the second with one row), dilation up to 32 >= H
+    (45, 22, None, 20, 40, 2),      # dilation 64 and 128 >= W: only the centre column of taps can touch the map
+])
+def test_fp32_conv_kernels_on_shapes_outside_the_zoo(dev, C, n_layers, pool, T, F, B):
+    """The three fp32 convolution kernels pick their geometry (units per CTA, input maps per chunk, row pitch, register
+    window or aligned taps, fallback when the weights do not fit) from the layer shape: shapes the model zoo never
+    produces, against the CPU oracle, and resident-weight kernels against the tile kernel bit for bit."""
+    from honk2_b200.class_registry import find_cls
+    cfg = {"n_layers": n_layers, "n_feature_maps": C, "use_dilation": True, "n_labels": 7}
+    if pool is not None:
+        cfg["pool"] = pool
+        cfg["use_dilation"] = False
+    torch.manual_seed(C * 1000 + n_layers)
+    m = find_cls("model.ResNet")(dict(cfg))
+    m.eval()
+    sd = m.state_dict()
+    synth.harden_(sd)
+    sdc = {k: v.clone() for k, v in sd.items()}
+    x = torch.randn(B, T, F, generator=torch.Generator().manual_seed(T * F)) * 3.0
+    ref = model_ref.forward("ResNet", sdc, cfg, x).numpy()
+    m = m.to(dev)
+    with torch.no_grad():
+        y = m(x.to(dev))
+    assert logit_err(y.cpu().numpy(), ref) <= LOGIT_TOL, logit_err(y.cpu().numpy(), ref)
+    import os
+    os.environ["HONK2_F32_RESIDENT"] = "0"
+    try:
+        m2 = find_cls("model.ResNet")(dict(cfg))
+        m2.eval()
+        m2.load_state_dict(sdc)
+        m2 = m2.to(dev)
+        with torch.no_grad():
+            y2 = m2(x.to(dev))
+    finally:
+        del os.environ["HONK2_F32_RESIDENT"]
+    assert torch.equal(y, y2)
+
+
 def test_bf16_column_sweep_kernel_matches_position_major_kernel_at_full_batch(dev, monkeypatch):
     """BASELINE size (8192 x 1 s): the two whole-network tensor-core kernels (column sweep, resnet_sweep.cuh;
     position major, resnet_fused.cuh) compute the same network from the same bf16 operands and differ only in the
