@@ -45,6 +45,7 @@ struct ConvGenF32 {
   float* y;
   int64_t B;
   int Cin, H, W, Cout, KH, KW, SH, SW;
+  int row_kernel = 1;   // 0: never the persistent row-tile kernel (HONK2_F32_RESIDENT=0, read per model handle)
 };
 int launch_conv_gen_f32(const ConvGenF32& a, cudaStream_t st);
 
@@ -52,9 +53,10 @@ int launch_conv_gen_f32(const ConvGenF32& a, cudaStream_t st);
 int launch_maxpool_f32(const float* x, float* y, int64_t planes, int H, int W, int kh, int kw,
                        cudaStream_t st);
 
-// Linear: y[M][N] = x[M][K] . w[N][K]^T + bias[N] (cnn.py:95-106).
+// Linear: y[M][N] = x[M][K] . w[N][K]^T + bias[N] (cnn.py:95-106).  `scratch` (optional, `scratch_floats` floats, must not
+// overlap x or y): room for split-K partial sums when the reduction is long and the output small.
 int launch_linear_f32(const float* x, const float* w, const float* bias, float* y, int64_t M, int N,
-                      int K, cudaStream_t st);
+                      int K, float* scratch, size_t scratch_floats, cudaStream_t st);
 
 // ---- bf16 tensor-core path (conv_tc.cu); activations are [B][H][W][48|...] bf16 --------------
 struct TcPlan;  // opaque, owned by the model

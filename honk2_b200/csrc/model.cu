@@ -281,6 +281,7 @@ extern "C" int kws_cnn_create(const kws_cnn_config* cfg, kws_model_t** out) {
   kws_model* m = new kws_model();
   m->kind = KIND_CNN;
   m->cc = c;
+  { const char* e = getenv("HONK2_F32_RESIDENT"); m->f32_resident = !(e && e[0] == '0'); }
   // utils/torch_utils.py:29-65 (floor mode, no padding, dilation 1)
   m->c_h0 = (c.time - c.conv0_kh) / c.conv0_sh + 1;
   m->c_w0 = (c.freq - c.conv0_kw) / c.conv0_sw + 1;
@@ -403,7 +404,7 @@ static int64_t cnn_max_act(const Model* m) {
 
 static size_t cnn_ws_f32(const Model* m, int64_t B, int64_t* chunk_out) {
   const int64_t per = cnn_max_act(m) * (int64_t)sizeof(float);
-  int64_t chunk = m->chunk[KWS_FP32] > 0 ? m->chunk[KWS_FP32] : 256;
+  int64_t chunk = m->chunk[KWS_FP32] > 0 ? m->chunk[KWS_FP32] : 1024;   // (~1.4 GB of scratch for cnn-trad-fpool3)
   if (chunk > B) chunk = B;
   if (chunk < 1) chunk = 1;
   if (chunk_out) *chunk_out = chunk;
@@ -426,6 +427,7 @@ static int cnn_forward_f32(Model* m, const float* feat, int64_t B, int T, int F,
     const int64_t nb = min(chunk, B - b0);
     int cur = 0;
     ConvGenF32 a;
+    a.row_kernel = m->f32_resident ? 1 : 0;
     a.x = feat + b0 * (int64_t)T * F; a.wt = m->c_conv0_w; a.bias = m->c_conv0_b; a.y = buf[cur];
     a.B = nb; a.Cin = 1; a.H = T; a.W = F; a.Cout = c.conv0_out;
     a.KH = c.conv0_kh; a.KW = c.conv0_kw; a.SH = c.conv0_sh; a.SW = c.conv0_sw;
@@ -452,8 +454,13 @@ static int cnn_forward_f32(Model* m, const float* feat, int64_t B, int T, int F,
     for (int i = 0; i < 4; ++i) {
       if (m->c_lin_out[i] <= 0) continue;
       float* dst = (i == 3) ? logits + b0 * c.n_labels : buf[cur ^ 1];
+      // the rest of the output buffer holds the split-K partial sums of a long reduction (the first Linear: K = 37376)
+      const size_t out_floats = (size_t)nb * m->c_lin_out[i];
+      float* scratch = (i == 3) ? nullptr : buf[cur ^ 1] + round_up<size_t>(out_floats, 64);
+      const size_t scratch_floats = (i == 3) ? 0 : need / 2 / sizeof(float) - round_up<size_t>(out_floats, 64);
       m->prof.tick(1, st);
-      KWS_TRY(launch_linear_f32(buf[cur], m->c_lin_w[i], m->c_lin_b[i], dst, nb, m->c_lin_out[i], m->c_lin_in[i], st));
+      KWS_TRY(launch_linear_f32(buf[cur], m->c_lin_w[i], m->c_lin_b[i], dst, nb, m->c_lin_out[i], m->c_lin_in[i], scratch,
+                                scratch_floats, st));
       cur ^= 1;
     }
   }

@@ -604,6 +604,26 @@ def test_fp32_resident_weight_kernel_matches_tile_kernel(dev, monkeypatch, name,
     assert logit_err(y_long, model_golden[f"{name}/hardened/logits_long"]) <= LOGIT_TOL
 
 
+@pytest.mark.parametrize("name", [n for n in MODEL_ZOO if n.startswith("cnn")])
+def test_fp32_cnn_row_kernel_matches_generic_kernel(dev, monkeypatch, name):
+    """The stride-1 convolutions with 4 or 8 kernel columns run on the persistent row-tile kernel (conv_row_f32_kernel);
+    HONK2_F32_RESIDENT=0 keeps every convolution on the generic one-tile-per-CTA kernel.  Same order of the fp32
+    additions: bit-identical logits for every member of the CNN family (those without such a layer run the generic kernel
+    either way), on a ragged batch, and against the oracle."""
+    monkeypatch.setenv("HONK2_F32_RESIDENT", "0")
+    m_gen, sd = gpu_model(name, "hardened", dev)
+    monkeypatch.setenv("HONK2_F32_RESIDENT", "1")
+    m_row, _ = gpu_model(name, "hardened", dev)
+    feats = mfcc_ref.compute_mfccs_batch(synth.noisy_dataset_like(19, seed=31))
+    x = torch.from_numpy(feats).to(dev)
+    with torch.no_grad():
+        y_gen, y_row = m_gen(x), m_row(x)
+    assert torch.equal(y_gen, y_row)
+    kind, cfg = model_config(name)
+    ref = model_ref.forward(kind, sd, cfg, torch.from_numpy(feats)).numpy()
+    assert logit_err(y_row.cpu().numpy(), ref) <= LOGIT_TOL
+
+
 @pytest.mark.parametrize("C,n_layers,pool,T,F,B", [
     (45, 13, None, 37, 24, 5),      # row kernel, 3 column blocks, ragged last unit (37 = 4 x 8 + 5), dilation up to 16
     (30, 7, None, 64, 48, 3),       # 30 maps (Q = 10, 3 groups), 48 columns, dilation up to 4

@@ -1,0 +1,8 @@
+# CNN family fp32: persistent row-tile convolution kernel vs the generic kernel (bit identity, oracle), throughput
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "cnn or fp32_logits_match" > gpurun_out/r3p_pytest.log 2>&1
+echo "rc=$?" >> gpurun_out/r3p_pytest.log
+B="python bench.py --precision fp32 --steps 3 --warmup 3 --no-cpu-baseline --no-second-mode --no-parity --no-other-configs --model cnn-trad-fpool3 --batch 4096"
+HONK2_F32_RESIDENT=0 timeout 600 $B > gpurun_out/r3p_bench_cnn_0.log 2> gpurun_out/r3p_bench_cnn_0.err
+HONK2_F32_RESIDENT=1 timeout 600 $B > gpurun_out/r3p_bench_cnn_1.log 2> gpurun_out/r3p_bench_cnn_1.err
+echo finished
