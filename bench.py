@@ -452,6 +452,7 @@ def main():
                 ("res26", "bf16", 8192, 16000, "configs[2]"), ("res15_narrow", "bf16", 8192, 16000, "configs[2]"),
                 ("res15_narrow", "fp32", 2048, 16000, "configs[2], CUDA-core path"),
                 ("cnn-trad-fpool3", "bf16", 8192, 16000, "configs[3]"),
+                ("cnn-trad-fpool3", "fp32", 4096, 16000, "configs[3], CUDA-core parity mode"),
                 ("res15", "bf16", 1024, 144000, "configs[4], one GPU's view: hey_snips-shaped 9 s clips"),
                 ("hey_snips_res26", "bf16", 256, 144000, "configs[2], the deep dilated stack (24 layers, dilation <= 128) at its own 901x40 shape")]
         for name, prec, nb, ns, tag in plan:
