@@ -2,9 +2,10 @@
 // Activations are planar [B][C][H][W] float32 like torch, so `x.view(B, -1)` (cnn.py:93) is the
 // buffer itself.
 //
-//   conv_gen_f32_kernel  Conv2d(stride, no padding, bias) + ReLU   /root/reference/model/cnn.py:82-83,87-88
+//   conv_row_f32_kernel  Conv2d(stride 1, 4 or 8 kernel columns, bias) + ReLU: persistent row-tile kernel (cnn-trad-fpool3's layers)
+//   conv_gen_f32_kernel  Conv2d(stride, no padding, bias) + ReLU   /root/reference/model/cnn.py:82-83,87-88 (every other shape)
 //   maxpool_f32_kernel   MaxPool2d(stride = kernel, floor)         /root/reference/model/cnn.py:85,91
-//   linear_f32_kernel    Linear                                    /root/reference/model/cnn.py:95-106
+//   linear_f32_kernel    Linear (split-K + linear_reduce_f32_kernel for long reductions)   /root/reference/model/cnn.py:95-106
 #include <algorithm>
 #include "kernels.cuh"
 

@@ -1,10 +1,12 @@
-// fp32 CUDA-core kernels of the ResNet path (parity mode, and the final path for the 19-map
-// "-narrow" nets and the 1-channel conv_0).  Activations are planar [B][C][H][W] float32, the
-// same order torch uses, so every intermediate can be compared with the reference module.
+// fp32 CUDA-core kernels of the ResNet path: the reference arithmetic (parity mode).  Activations are planar
+// [B][C][H][W] float32, the same order torch uses, so every intermediate can be compared with the reference module.
 //
-//   conv0_f32_kernel    conv_0 + ReLU + AvgPool          /root/reference/model/resnet.py:40-44
-//   conv3x3_f32_kernel  conv_i + ReLU + skip + BatchNorm /root/reference/model/resnet.py:48-55
-//   tail_f32_kernel     mean over H*W + Linear           /root/reference/model/resnet.py:57-59
+//   conv0_f32_kernel         conv_0 + ReLU + AvgPool          /root/reference/model/resnet.py:40-44
+//   conv3x3_f32_row_kernel   conv_i + ReLU + skip + BatchNorm /root/reference/model/resnet.py:48-55: persistent, the layer's weights
+//                            resident in shared memory, 1 row x 8 columns x Q maps per thread (maps whose width is a multiple of 8)
+//   conv3x3_f32_res_kernel   the same, 8 rows x 1 column x Q maps per thread (the pooled maps: 13 and 20 columns)
+//   conv3x3_f32_kernel       the same, one 8-row tile per CTA (weights that do not fit in shared memory; HONK2_F32_RESIDENT=0)
+//   tail_f32_kernel          mean over H*W + Linear           /root/reference/model/resnet.py:57-59
 #include <algorithm>
 #include <cstdlib>
 #include "kernels.cuh"
