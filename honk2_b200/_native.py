@@ -53,6 +53,8 @@ SIGNATURES = {
     "kws_mfcc_stream_scratch_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int, C.c_int]),
     "kws_mfcc_stream_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_size_t, C.c_void_p]),
+    "kws_mfcc_stream_forward_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_void_p, C.c_size_t, C.c_void_p]),
     "kws_resnet_create": (C.c_int, [C.POINTER(ResNetConfig), C.POINTER(C.c_void_p)]),
     "kws_resnet_set_weights": (C.c_int, [C.c_void_p, C.POINTER(ResNetWeights), C.c_void_p]),
     "kws_cnn_create": (C.c_int, [C.POINTER(CnnConfig), C.POINTER(C.c_void_p)]),

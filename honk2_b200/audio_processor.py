@@ -103,7 +103,8 @@ class AudioProcessor(object):
     def compute_mfccs_stream(self, stream, window_size=16000, shift_size=160, first=0, count=None, out=None):
         """Features of the sliding windows of one audio stream, without materialising the windows.
 
-        stream: CUDA float32 [L]; window k = stream[k*shift_size : k*shift_size + window_size], exactly what
+        stream: CUDA float32 [L] (or int16 PCM, converted while staging: bit-identical features); window k =
+        stream[k*shift_size : k*shift_size + window_size], exactly what
         StreamingDataset.__getitem__ hands to collate_fn (dataset/dataset_utils.py:72, audio_data_loader.py:26-29;
         gsc_dev_config.json:62-63: 16000 / 160 samples).  Returns CUDA float32 [count, T, n_mels] for windows
         first .. first+count-1 (default: all StreamingDataset.num_samples of them), bit-identical to
@@ -115,7 +116,8 @@ class AudioProcessor(object):
             raise ValueError("compute_mfccs_stream expects a 1-D stream")
         if window_size < 1 or shift_size < 1:
             raise ValueError("window_size and shift_size must be positive")
-        if stream.dtype != torch.float32:
+        pcm16 = stream.dtype == torch.int16
+        if not pcm16 and stream.dtype != torch.float32:
             stream = stream.float()
         stream = stream.contiguous()
         total = self.n_stream_windows(stream.numel(), window_size, shift_size)
@@ -135,11 +137,12 @@ class AudioProcessor(object):
         fe = self._frontend(stream.device)
         need = lib.kws_mfcc_stream_scratch_bytes(fe, count, window_size, shift_size)
         scratch = torch.empty(max(need, 16), dtype=torch.uint8, device=stream.device)
-        base = stream.data_ptr() + 4 * first * shift_size
+        base = stream.data_ptr() + stream.element_size() * first * shift_size
+        fn = lib.kws_mfcc_stream_forward_pcm16 if pcm16 else lib.kws_mfcc_stream_forward
         with torch.cuda.device(stream.device):
-            _native.check(lib.kws_mfcc_stream_forward(fe, C.c_void_p(base), count, window_size, shift_size,
-                                                      C.c_void_p(out.data_ptr()), C.c_void_p(scratch.data_ptr()),
-                                                      need, _stream_ptr(stream.device)), "kws_mfcc_stream_forward")
+            _native.check(fn(fe, C.c_void_p(base), count, window_size, shift_size, C.c_void_p(out.data_ptr()),
+                             C.c_void_p(scratch.data_ptr()), need, _stream_ptr(stream.device)),
+                          "kws_mfcc_stream_forward_pcm16" if pcm16 else "kws_mfcc_stream_forward")
         return out
 
     # ---- reference API -------------------------------------------------------------------

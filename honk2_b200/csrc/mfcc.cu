@@ -436,6 +436,8 @@ extern "C" int kws_frontend_create(int sr, int n_mels, float f_min, float f_max,
     e = cudaFuncSetAttribute(mfcc_kernel<false, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(mfcc_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes_edges);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(mfcc_kernel<true, int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fe->smem_bytes_edges);
   if (e != cudaSuccess) {
     set_error("kws_frontend_create: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     cudaFree(fe->dev_blob);
@@ -496,8 +498,9 @@ extern "C" size_t kws_mfcc_stream_scratch_bytes(const kws_frontend_t* fe, int64_
   return (size_t)(1 + span / kHop) * fe->n_mels * sizeof(float);
 }
 
-extern "C" int kws_mfcc_stream_forward(const kws_frontend_t* fe, const float* wav, int64_t n_windows, int window,
-                                       int shift, float* feat, void* scratch, size_t scratch_bytes, void* stream) {
+template <typename SMP>
+static int mfcc_stream_forward_any(const kws_frontend_t* fe, const SMP* wav, int64_t n_windows, int window,
+                                   int shift, float* feat, void* scratch, size_t scratch_bytes, void* stream) {
   KWS_REQUIRE(fe != nullptr, "kws_mfcc_stream_forward: frontend is null");
   KWS_REQUIRE(n_windows >= 0, "kws_mfcc_stream_forward: negative window count");
   KWS_REQUIRE(window > kNfft / 2, "kws_mfcc_stream_forward: need more than %d samples per window (got %d)",
@@ -513,7 +516,7 @@ extern "C" int kws_mfcc_stream_forward(const kws_frontend_t* fe, const float* wa
     // windows do not share frames (or have no interior frame): every window in full, read in place from the stream
     const int64_t blocks = n_windows * tiles;
     KWS_REQUIRE(blocks < (int64_t)2147483647, "kws_mfcc_stream_forward: too many windows for one launch");
-    mfcc_kernel<false, float><<<(unsigned)blocks, kMfccThreads, fe->smem_bytes, st>>>(
+    mfcc_kernel<false, SMP><<<(unsigned)blocks, kMfccThreads, fe->smem_bytes, st>>>(
         fe->t, wav, (int64_t)shift, n_windows, window, T, tiles, feat);
     KWS_CHECK_LAUNCH();
     return KWS_OK;
@@ -526,11 +529,11 @@ extern "C" int kws_mfcc_stream_forward(const kws_frontend_t* fe, const float* wa
   // 1) the frame table of the whole span as ONE clip: rows 2 .. J-3 do not touch its reflect padding
   float* S = static_cast<float*>(scratch);
   const int J = 1 + (int)(span / kHop);
-  mfcc_kernel<false, float><<<(unsigned)ceil_div(J, kFramesPerCta), kMfccThreads, fe->smem_bytes, st>>>(
+  mfcc_kernel<false, SMP><<<(unsigned)ceil_div(J, kFramesPerCta), kMfccThreads, fe->smem_bytes, st>>>(
       fe->t, wav, span, (int64_t)1, (int)span, J, ceil_div(J, kFramesPerCta), S);
   KWS_CHECK_LAUNCH();
   // 2) the four frames per window that do (reflect padding at the WINDOW's edges, audio_processor.py:19-26 per window)
-  mfcc_kernel<true, float><<<(unsigned)ceil_div<int64_t>(n_windows, 4), kMfccThreads, fe->smem_bytes_edges, st>>>(
+  mfcc_kernel<true, SMP><<<(unsigned)ceil_div<int64_t>(n_windows, 4), kMfccThreads, fe->smem_bytes_edges, st>>>(
       fe->t, wav, (int64_t)shift, n_windows, window, T, 1, feat);
   KWS_CHECK_LAUNCH();
   // 3) interior frames: copies of table rows
@@ -546,4 +549,14 @@ extern "C" int kws_mfcc_stream_forward(const kws_frontend_t* fe, const float* wa
     mfcc_stream_gather_kernel<float><<<grid, 256, 0, st>>>(S, n_windows, T, m, row_v, feat);
   KWS_CHECK_LAUNCH();
   return KWS_OK;
+}
+
+extern "C" int kws_mfcc_stream_forward(const kws_frontend_t* fe, const float* wav, int64_t n_windows, int window,
+                                       int shift, float* feat, void* scratch, size_t scratch_bytes, void* stream) {
+  return mfcc_stream_forward_any<float>(fe, wav, n_windows, window, shift, feat, scratch, scratch_bytes, stream);
+}
+
+extern "C" int kws_mfcc_stream_forward_pcm16(const kws_frontend_t* fe, const int16_t* wav, int64_t n_windows, int window,
+                                             int shift, float* feat, void* scratch, size_t scratch_bytes, void* stream) {
+  return mfcc_stream_forward_any<int16_t>(fe, wav, n_windows, window, shift, feat, scratch, scratch_bytes, stream);
 }

@@ -78,6 +78,9 @@ int kws_mfcc_forward_pcm16(const kws_frontend_t* fe, const int16_t* wav, int64_t
 size_t kws_mfcc_stream_scratch_bytes(const kws_frontend_t* fe, int64_t n_windows, int window, int shift);
 int kws_mfcc_stream_forward(const kws_frontend_t* fe, const float* wav, int64_t n_windows, int window, int shift,
                             float* feat, void* scratch, size_t scratch_bytes, void* stream);
+/* The same on an int16 PCM stream (see kws_mfcc_forward_pcm16); same scratch size, bit-identical features. */
+int kws_mfcc_stream_forward_pcm16(const kws_frontend_t* fe, const int16_t* wav, int64_t n_windows, int window, int shift,
+                                  float* feat, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- models: replace model.ResNet / model.CNN ---------------------------------------------
  * kws_resnet_create <- ResNet.__init__ (model/resnet.py:11-36); pool_h = pool_w = 0 when the

@@ -119,6 +119,22 @@ def test_mfcc_stream_windows_equal_materialised_windows(dev, window, shift):
     assert scaled_err(got[ks].cpu().numpy(), ref) <= MFCC_TOL
 
 
+@pytest.mark.parametrize("window,shift", [(16000, 160), (16000, 100), (8000, 320), (144000, 1600)])
+def test_mfcc_stream_pcm16_equals_float_stream(dev, window, shift):
+    """An int16 PCM stream through the streaming front-end (shared frames, edge frames, row copies, or the unshared path
+    for a shift that is not a multiple of the hop): bit-identical to the float32 stream of the same samples, incl. a
+    sub-range that starts at an odd sample offset."""
+    ap = AudioProcessor()
+    n_win = 21 if window < 100000 else 4
+    L = (n_win + 1) * shift + window - 1
+    pcm = np.random.default_rng(window + shift).integers(-20000, 20000, size=L, dtype=np.int16)
+    s16 = torch.from_numpy(pcm).to(dev)
+    sf = torch.from_numpy(pcm.astype(np.float32) / 32768.0).to(dev)
+    a, b = ap.compute_mfccs_stream(s16, window, shift), ap.compute_mfccs_stream(sf, window, shift)
+    assert a.shape == (n_win, 1 + window // 160, 40) and torch.equal(a, b)
+    assert torch.equal(ap.compute_mfccs_stream(s16, window, shift, first=1, count=3), b[1:4])
+
+
 def test_mfcc_stream_at_batch_size_and_argument_errors(dev):
     """8192 windows of 1 s at a 10 ms shift (gsc_dev_config.json:62-63) from a 83 s stream: 4 frames per window are
     computed per window, the other 97 come from the 8293-row stream frame table."""
