@@ -1249,10 +1249,13 @@ conv0_pool_pack_kernel(const float* __restrict__ feat, const float* __restrict__
     }
   constexpr float inv = 1.f / (float)(PH * PW);
   const int swl = ((dmax + row) >> 2) & 1;
+  // (a warp whose 32 items are all gap rows / past the batch only stores zeros; the pad channels C .. CP-1 are zeros too)
+  const bool warp_live = __any_sync(0xffffffffu, live);
   for (int kc = 0; kc < NKC; ++kc) {
     float out[16];
 #pragma unroll
     for (int cl = 0; cl < 16; ++cl) {
+      if (!warp_live || 16 * kc + cl >= C) { out[cl] = 0.f; continue; }
       const float* wc = s_w + (16 * kc + cl) * 12;
       const float4 wa = *reinterpret_cast<const float4*>(wc);
       const float4 wb = *reinterpret_cast<const float4*>(wc + 4);
