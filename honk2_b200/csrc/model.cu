@@ -234,6 +234,8 @@ static int resnet_forward_f32(Model* m, const float* feat, int64_t B, int T, int
   float* A0 = reinterpret_cast<float*>(static_cast<char*>(ws) + buf);
   float* A1 = reinterpret_cast<float*>(static_cast<char*>(ws) + 2 * buf);
   const int ph = c.pool_h > 0 ? c.pool_h : 1, pw = c.pool_w > 0 ? c.pool_w : 1;
+  // equal sub-batches (2048 utterances = 3 x 683, not 985 + 985 + 78): the persistent kernels' last wave stays full
+  if (B > chunk) chunk = ceil_div<int64_t>(B, ceil_div<int64_t>(B, chunk));
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     const int64_t nb = min(chunk, B - b0);
     m->prof.tick(1, st);
